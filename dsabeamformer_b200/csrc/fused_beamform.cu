@@ -1,0 +1,456 @@
+// fused_beamform.cu -- ONE kernel for unpack -> beamform -> detect/average.
+//
+// Replaces the reference's three-step sequence (and its two HBM round trips)
+//   expand_input                      /root/reference/src/beamformer.cuh:66-109
+//   cublasGemmStridedBatchedEx        /root/reference/src/beamformer.cu:470-477
+//   detect_sum                        /root/reference/src/beamformer.cuh:115-155
+// for a whole block of chunks per launch.
+//
+// Math.  Per channel f the reference computes C = (1/127) W_f X_f (complex) and
+// sums |C|^2 over G = n_pol*n_averaging consecutive columns.  Here the complex
+// product is two real int8 GEMMs on the 5th-gen tensor cores (tcgen05.mma
+// kind::i8, int32 accumulators in TMEM):
+//     [Vre; Vim] = [[Wre, -Wim], [Wim, Wre]] [Xre; Xim]
+// A' (weights) rows are interleaved (row 2i = re of beam i, row 2i+1 = im), K' =
+// 2*64 antennas = 128 bytes = exactly one SWIZZLE_128B row, so one M=128 tile is
+// 64 beams and a 256-beam channel is 4 resident 16 KB tiles.  X is NOT shifted
+// down when unpacked: the nibbles are left in the high half of each byte
+// (x' = 16 x), so unpacking is 2 LOP3 + 1 SHF per 4 samples; V' = 16 V stays
+// < 2^22, and the factor 256 in the power is folded into the output scale.
+//
+// Data flow per CTA (persistent, one CTA per SM, contiguous range of work items;
+// item = (channel, 256-column tile), 4 M-tiles per item):
+//   warp 0      TMA producer: cp.async.bulk packed voltages -> staging ring (4 x 16 KB)
+//   warp 1      MMA issuer (one thread): 4 x tcgen05.mma M128 N256 K32 per M-tile,
+//               TMEM accumulators double-buffered (2 x 256 columns)
+//   warp 2      weights loader (cp.async.bulk of the pre-swizzled A' tiles) + TMEM alloc
+//   warp 3      idle
+//   warps 4-11  epilogue: tcgen05.ld -> square/accumulate over G columns -> one
+//               shuffle to add re^2+im^2 rows -> coalesced float stores
+//   warps 12-15 unpack: staging -> sign-preserving nibble split -> SW128 K-major B' tile
+// Voltages are read from HBM once, weights once per (CTA, channel); nothing but
+// the final float power is written.
+#include "fused_beamform.cuh"
+#include "sm100_ptx.cuh"
+#include <type_traits>
+
+namespace dsabf {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kTileN = 256;              // columns per work item (UMMA N)
+constexpr int kRowBytes = 128;           // K' bytes per row = 2 * 64 antennas
+constexpr int kATileBytes = 128 * kRowBytes;   // 16 KB: one M=128 weights tile
+constexpr int kBTileBytes = kTileN * kRowBytes; // 32 KB: unpacked voltages tile
+constexpr int kStageBytes = kTileN * 64;        // 16 KB: packed voltages tile
+constexpr int kStages = 4;
+constexpr int kMaxMT = 4;
+constexpr int kAccCols = 256;            // TMEM columns per accumulator stage
+constexpr int kTmemCols = 512;
+
+constexpr int kEpiWarp0 = 4, kNumEpiWarps = 8;
+constexpr int kUnpackWarp0 = 12, kNumUnpackWarps = 4;
+
+struct __align__(1024) Smem {
+    uint8_t a[kMaxMT][kATileBytes];      // 64 KB  resident weights of the current channel
+    uint8_t b[2][kBTileBytes];           // 64 KB  unpacked voltages, double buffered
+    uint8_t stg[kStages][kStageBytes];   // 64 KB  packed voltages ring
+    uint64_t stg_full[kStages], stg_empty[kStages];
+    uint64_t b_full[2], b_empty[2];
+    uint64_t a_full[kMaxMT], a_empty[kMaxMT];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+// square-accumulate in the two supported arithmetic modes
+template <bool EXACT> struct Acc;
+template <> struct Acc<true> {
+    long long s;
+    __device__ __forceinline__ void zero() { s = 0; }
+    __device__ __forceinline__ void add(int v) { asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s) : "r"(v)); }
+};
+template <> struct Acc<false> {
+    float s;
+    __device__ __forceinline__ void zero() { s = 0.f; }
+    __device__ __forceinline__ void add(int v) { float f = __int2float_rn(v); s = fmaf(f, f, s); }
+};
+
+// Work-item geometry shared by all roles.
+struct Geom {
+    int n_chan, n_chunks, cpc, n_tiles, n_cols_total;
+    __device__ __forceinline__ Geom(const FusedParams &p)
+        : n_chan(p.n_chan), n_chunks(p.n_chunks), cpc(p.cols_per_chunk), n_tiles(p.n_tiles),
+          n_cols_total(p.n_chunks * p.cols_per_chunk) {}
+};
+
+// Per-(row, M-tile) epilogue state of one thread.
+template <bool EXACT> struct EpiCtx {
+    using sum_t = typename std::conditional<EXACT, long long, float>::type;
+    Acc<EXACT> acc;       // running sum of squares of the current group of G columns
+    sum_t pend;           // finished even group waiting for the odd group of its pair
+    int colbase;          // global column of this warp's first TMEM column
+    int n_cols_total;
+    int lane_odd;         // odd lanes hold im rows
+    size_t out_base, out_tstride;
+    int32_t *vd;          // voltage dump base for this row (nullptr = off)
+    size_t vd_cstride;
+};
+
+template <int G, bool EXACT>
+__device__ __forceinline__ void epi_store(const EpiCtx<EXACT> &c, const FusedParams &p, typename EpiCtx<EXACT>::sum_t tot, int col)
+{
+    if (col < c.n_cols_total) {
+        const size_t o = c.out_base + (size_t)(col / G) * c.out_tstride;
+        p.out[o] = (float)tot * p.scale;
+        if (EXACT) {
+            if (p.pdump) p.pdump[o] = (long long)tot >> 8;
+        }
+    }
+}
+
+// 32 accumulator columns [BLK*32, BLK*32+32) of this warp's 128: square, sum per
+// group of G columns, and on every second finished group exchange with the lane
+// holding the other component (re rows = even lanes, im rows = odd lanes): even
+// lanes finish the even group of the pair, odd lanes the odd group, so one
+// shuffle yields two outputs and a warp stores 2 x 64 contiguous bytes.
+template <int G, bool EXACT, int BLK>
+__device__ __forceinline__ void epi_block(EpiCtx<EXACT> &c, const FusedParams &p, const uint32_t (&v)[32])
+{
+    if (c.vd != nullptr) {
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) {
+            const int col = c.colbase + BLK * 32 + jj;
+            if (col < c.n_cols_total) c.vd[(size_t)col * c.vd_cstride] = ((int)v[jj]) >> 4;
+        }
+    }
+    constexpr int kGroups = 128 / G;
+#pragma unroll
+    for (int jj = 0; jj < 32; jj++) {
+        c.acc.add((int)v[jj]);
+        const int cl = BLK * 32 + jj;              // compile-time after unrolling
+        if (((cl + 1) % G) == 0) {
+            const int grp = cl / G;
+            const auto sgrp = c.acc.s;
+            c.acc.zero();
+            if (kGroups == 1) {
+                const auto tot = sgrp + __shfl_xor_sync(0xffffffffu, sgrp, 1);
+                if (!c.lane_odd) epi_store<G, EXACT>(c, p, tot, c.colbase + cl);
+            } else if ((grp & 1) == 0) {
+                c.pend = sgrp;
+            } else {
+                const auto send = c.lane_odd ? c.pend : sgrp;
+                const auto mine = c.lane_odd ? sgrp : c.pend;
+                const auto tot = mine + __shfl_xor_sync(0xffffffffu, send, 1);
+                epi_store<G, EXACT>(c, p, tot, c.colbase + cl - (c.lane_odd ? 0 : G));
+            }
+        }
+    }
+}
+
+template <int G, bool EXACT>
+__global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const FusedParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const Geom g(p);
+    const int mt = p.n_beams >> 6;
+
+    const long long items_total = (long long)g.n_chan * g.n_tiles;
+    const int item_begin = (int)((items_total * blockIdx.x) / gridDim.x);
+    const int item_end = (int)((items_total * (blockIdx.x + 1)) / gridDim.x);
+
+    // ---- one-time set-up ----
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; i++) { mbar_init(&sm.stg_full[i], 1); mbar_init(&sm.stg_empty[i], kNumUnpackWarps); }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&sm.b_full[i], kNumUnpackWarps); mbar_init(&sm.b_empty[i], 1);
+            mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps);
+        }
+        for (int i = 0; i < kMaxMT; i++) { mbar_init(&sm.a_full[i], 1); mbar_init(&sm.a_empty[i], 1); }
+        fence_mbar_init();
+    }
+    if (warp == 2) { tmem_alloc(&sm.tmem_base, kTmemCols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp == 0) {
+        // ================= TMA producer: packed voltages =================
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            for (int item = item_begin, it = 0; item < item_end; item++, it++) {
+                const int f = item / g.n_tiles, t = item - f * g.n_tiles;
+                const int s = it % kStages;
+                mbar_wait(&sm.stg_empty[s], ((it / kStages) & 1) ^ 1, 1);
+                const int col0 = t * kTileN;
+                if (g.cpc >= kTileN) {
+                    const int chunk = col0 / g.cpc, c_in = col0 - chunk * g.cpc;
+                    const uint8_t *src = p.packed + (((size_t)chunk * g.n_chan + f) * g.cpc + c_in) * 64;
+                    mbar_arrive_expect_tx(&sm.stg_full[s], kStageBytes);
+                    tma_bulk_g2s_hint(sm.stg[s], src, kStageBytes, &sm.stg_full[s], pol);
+                } else {
+                    const int per_tile = kTileN / g.cpc;
+                    const int chunk0 = t * per_tile;
+                    const int nseg = min(per_tile, g.n_chunks - chunk0);
+                    const uint32_t seg_bytes = g.cpc * 64;
+                    mbar_arrive_expect_tx(&sm.stg_full[s], seg_bytes * nseg);
+                    for (int k = 0; k < nseg; k++) {
+                        const uint8_t *src = p.packed + (((size_t)(chunk0 + k) * g.n_chan + f) * g.cpc) * 64;
+                        tma_bulk_g2s_hint(sm.stg[s] + k * seg_bytes, src, seg_bytes, &sm.stg_full[s], pol);
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ================= weights loader =================
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_last();
+            int cur_f = -1, ch = 0;
+            for (int item = item_begin; item < item_end; item++) {
+                const int f = item / g.n_tiles;
+                if (f == cur_f) continue;
+                cur_f = f;
+                for (int m = 0; m < mt; m++) {
+                    mbar_wait(&sm.a_empty[m], (ch & 1) ^ 1, 2);
+                    mbar_arrive_expect_tx(&sm.a_full[m], kATileBytes);
+                    tma_bulk_g2s_hint(sm.a[m], p.wprep + ((size_t)f * mt + m) * kATileBytes, kATileBytes, &sm.a_full[m], pol);
+                }
+                ch++;
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_i8(128, kTileN);
+            int cur_f = -1, ch = -1;
+            uint32_t acc_cnt = 0;
+            for (int item = item_begin, it = 0; item < item_end; item++, it++) {
+                const int f = item / g.n_tiles;
+                const bool new_ch = (f != cur_f);
+                if (new_ch) { cur_f = f; ch++; }
+                const bool last_of_ch = (item + 1 == item_end) || ((item + 1) / g.n_tiles != f);
+                const int buf = it & 1;
+                mbar_wait(&sm.b_full[buf], (it >> 1) & 1, 3);
+                tc_fence_after();
+                const uint64_t bdesc = make_desc_k_sw128(smem_u32(sm.b[buf]));
+                for (int m = 0; m < mt; m++) {
+                    if (new_ch) mbar_wait(&sm.a_full[m], ch & 1, 4);
+                    const uint32_t as = acc_cnt & 1;
+                    mbar_wait(&sm.acc_empty[as], ((acc_cnt >> 1) & 1) ^ 1, 5);
+                    tc_fence_after();
+                    const uint64_t adesc = make_desc_k_sw128(smem_u32(sm.a[m]));
+                    const uint32_t d = tmem_base + as * kAccCols;
+#pragma unroll
+                    for (int k = 0; k < kRowBytes / 32; k++)   // K = 32 bytes per instruction; +32 B = +2 in the descriptor
+                        mma_i8_ss(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0);
+                    tc_commit(&sm.acc_full[as]);
+                    if (last_of_ch) tc_commit(&sm.a_empty[m]);
+                    acc_cnt++;
+                }
+                tc_commit(&sm.b_empty[buf]);
+            }
+        }
+    } else if (warp >= kUnpackWarp0) {
+        // ================= unpack: 4-bit+4-bit -> int8 (x16), into SW128 K-major B' =================
+        const int uw = warp - kUnpackWarp0;
+        // lane -> (row r in an 8-column group, 16-byte antenna chunk c): chosen so that both the
+        // 16 B loads (64 B rows) and the swizzled 16 B stores (128 B rows) are bank-conflict free.
+        const int q = lane >> 3, j = lane & 7, c = j & 3;
+        const int r = (j < 4) ? q : (q ^ 5);
+        const uint32_t ld_off = r * 64 + c * 16;
+        const uint32_t st_re = r * 128 + ((c ^ r) << 4);
+        const uint32_t st_im = r * 128 + (((c + 4) ^ r) << 4);
+        for (int item = item_begin, it = 0; item < item_end; item++, it++) {
+            const int s = it % kStages, buf = it & 1;
+            mbar_wait(&sm.stg_full[s], (it / kStages) & 1, 6);
+            mbar_wait(&sm.b_empty[buf], ((it >> 1) & 1) ^ 1, 7);
+            const uint32_t src = smem_u32(sm.stg[s]) + ld_off;
+            const uint32_t dst = smem_u32(sm.b[buf]);
+#pragma unroll
+            for (int i = 0; i < (kTileN / 8) / kNumUnpackWarps; i++) {
+                const int grp = uw + i * kNumUnpackWarps;      // 8-column group
+                const uint4 v = lds128(src + grp * 512);
+                uint4 re, im;
+                re.x = v.x & 0xF0F0F0F0u; im.x = (v.x << 4) & 0xF0F0F0F0u;
+                re.y = v.y & 0xF0F0F0F0u; im.y = (v.y << 4) & 0xF0F0F0F0u;
+                re.z = v.z & 0xF0F0F0F0u; im.z = (v.z << 4) & 0xF0F0F0F0u;
+                re.w = v.w & 0xF0F0F0F0u; im.w = (v.w << 4) & 0xF0F0F0F0u;
+                sts128(dst + grp * 1024 + st_re, re);
+                sts128(dst + grp * 1024 + st_im, im);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&sm.b_full[buf]); mbar_arrive(&sm.stg_empty[s]); }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ================= epilogue: TMEM -> |V|^2 summed over G columns -> float power =================
+        const int ew = warp - kEpiWarp0;
+        const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                  // which 128 columns of the tile
+        const int row = quarter * 32 + lane;       // A' row: beam = row/2, component = row&1
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        uint32_t acc_cnt = 0;
+        for (int item = item_begin; item < item_end; item++) {
+            const int f = item / g.n_tiles, t = item - f * g.n_tiles;
+            const int colbase = t * kTileN + half * 128;    // first global column of this warp's half
+            for (int m = 0; m < mt; m++, acc_cnt++) {
+                const uint32_t as = acc_cnt & 1;
+                mbar_wait(&sm.acc_full[as], (acc_cnt >> 1) & 1, 8);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + lane_addr + as * kAccCols + half * 128;
+                const int beam0 = m * 64;
+
+                EpiCtx<EXACT> ctx;
+                ctx.acc.zero();
+                ctx.pend = 0;
+                ctx.colbase = colbase;
+                ctx.n_cols_total = g.n_cols_total;
+                ctx.lane_odd = lane & 1;
+                // out index of (output time 0, channel f, this row's beam); one output time = n_chan*n_beams floats
+                ctx.out_base = (size_t)f * p.n_beams + beam0 + (row >> 1);
+                ctx.out_tstride = (size_t)g.n_chan * p.n_beams;
+                ctx.vd = p.vdump ? p.vdump + ((size_t)f * g.n_cols_total * p.n_beams + beam0) * 2 + row : nullptr;
+                ctx.vd_cstride = (size_t)p.n_beams * 2;
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32(taddr, va);
+                tmem_ld_wait(va);
+                tmem_ld_32x32(taddr + 32, vb);
+                epi_block<G, EXACT, 0>(ctx, p, va);
+                tmem_ld_wait(vb);
+                tmem_ld_32x32(taddr + 64, va);
+                epi_block<G, EXACT, 1>(ctx, p, vb);
+                tmem_ld_wait(va);
+                tmem_ld_32x32(taddr + 96, vb);
+                epi_block<G, EXACT, 2>(ctx, p, va);
+                tmem_ld_wait(vb);
+                // all of this warp's TMEM reads of the stage are done: hand it back to the MMA
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.acc_empty[as]);
+                epi_block<G, EXACT, 3>(ctx, p, vb);
+            }
+        }
+    }
+
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+template <int G, bool EXACT>
+cudaError_t launch_one(const FusedParams &p, int grid, cudaStream_t stream)
+{
+    const size_t smem = sizeof(Smem) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fused_beamform_kernel<G, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    fused_beamform_kernel<G, EXACT><<<grid, kThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <bool EXACT>
+cudaError_t launch_g(const FusedParams &p, int grid, cudaStream_t stream)
+{
+    switch (p.group) {
+    case 2: return launch_one<2, EXACT>(p, grid, stream);
+    case 4: return launch_one<4, EXACT>(p, grid, stream);
+    case 8: return launch_one<8, EXACT>(p, grid, stream);
+    case 16: return launch_one<16, EXACT>(p, grid, stream);
+    case 32: return launch_one<32, EXACT>(p, grid, stream);
+    case 64: return launch_one<64, EXACT>(p, grid, stream);
+    case 128: return launch_one<128, EXACT>(p, grid, stream);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_fused_beamform(const FusedParams &p, bool exact, int num_sms, cudaStream_t stream)
+{
+    if (p.n_beams % 64 || p.n_beams < 64 || p.n_beams > 64 * kMaxMT) return cudaErrorInvalidValue;
+    if (p.cols_per_chunk % p.group) return cudaErrorInvalidValue;
+    if (!((p.cols_per_chunk >= kTileN && p.cols_per_chunk % kTileN == 0) || (kTileN % p.cols_per_chunk == 0)))
+        return cudaErrorInvalidValue;
+    const long long items = (long long)p.n_chan * p.n_tiles;
+    if (items <= 0) return cudaSuccess;
+    const int grid = (int)(items < num_sms ? items : num_sms);
+    return exact ? launch_g<true>(p, grid, stream) : launch_g<false>(p, grid, stream);
+}
+
+// ---------------------------------------------------------------------------
+// Weights re-layout: reference layout [chan][ant][beam][2] int8  ->  per (chan,
+// M-tile) a 16 KB K-major SWIZZLE_128B image of A' (row 2i = [Wre | -Wim] of beam
+// i, row 2i+1 = [Wim | Wre]), ready for a plain bulk copy into shared memory.
+__global__ void prep_weights_kernel(const int8_t *__restrict__ w, uint8_t *__restrict__ wprep, int n_chan, int n_ant, int n_beams,
+                                    int *__restrict__ bad)
+{
+    const int mt = n_beams >> 6;
+    const size_t total = (size_t)n_chan * mt * 128 * 128;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int kb = idx & 127;                  // logical K byte
+        const int r = (idx >> 7) & 127;            // row in the M tile
+        const size_t fm = idx >> 14;
+        const int m = fm % mt;
+        const int f = fm / mt;
+        const int beam = m * 64 + (r >> 1);
+        const int comp = r & 1;                    // 0: re row, 1: im row
+        const int a = kb & 63;
+        const int hi = kb >> 6;                    // 0: multiplies Xre, 1: multiplies Xim
+        const int8_t *wp = w + (((size_t)f * n_ant + a) * n_beams + beam) * 2;
+        const int wre = wp[0], wim = wp[1];
+        if (wre == -128 || wim == -128) *bad = 1;
+        int val;
+        if (comp == 0) val = hi ? -wim : wre;
+        else           val = hi ? wre : wim;
+        const size_t off = fm * kATileBytes + (size_t)(r >> 3) * 1024 + (r & 7) * 128 + ((((kb >> 4) ^ (r & 7))) << 4) + (kb & 15);
+        wprep[off] = (uint8_t)(int8_t)val;
+    }
+}
+
+cudaError_t launch_prep_weights(const int8_t *d_w, uint8_t *d_wprep, int n_chan, int n_ant, int n_beams, int *d_bad, cudaStream_t stream)
+{
+    if (n_ant != 64) return cudaErrorInvalidValue;
+    prep_weights_kernel<<<1184, 256, 0, stream>>>(d_w, d_wprep, n_chan, n_ant, n_beams, d_bad);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// DM-0 "dedispersion" of output time 0 of every chunk (the DEBUG cublasSgemv,
+// /root/reference/src/beamformer.cu:498-504): ded[chunk][b] = sum_f out[chunk*n_out_per_chunk][f][b].
+__global__ void dm0_kernel(const float *__restrict__ out, float *__restrict__ ded, int n_chunks, int n_out_per_chunk, int n_chan, int n_beams)
+{
+    const int chunk = blockIdx.x;
+    const float *base = out + (size_t)chunk * n_out_per_chunk * n_chan * n_beams;
+    for (int b = threadIdx.x; b < n_beams; b += blockDim.x) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int f = 0;
+        for (; f + 3 < n_chan; f += 4) {
+            s0 += base[(size_t)f * n_beams + b];
+            s1 += base[(size_t)(f + 1) * n_beams + b];
+            s2 += base[(size_t)(f + 2) * n_beams + b];
+            s3 += base[(size_t)(f + 3) * n_beams + b];
+        }
+        for (; f < n_chan; f++) s0 += base[(size_t)f * n_beams + b];
+        ded[(size_t)chunk * n_beams + b] = (s0 + s1) + (s2 + s3);
+    }
+}
+
+cudaError_t launch_dm0(const float *d_out, float *d_ded, int n_chunks, int n_out_per_chunk, int n_chan, int n_beams, cudaStream_t stream)
+{
+    if (n_chunks <= 0) return cudaSuccess;
+    dm0_kernel<<<n_chunks, 256, 0, stream>>>(d_out, d_ded, n_chunks, n_out_per_chunk, n_chan, n_beams);
+    return cudaGetLastError();
+}
+
+}  // namespace dsabf
