@@ -216,7 +216,7 @@ int dsabf_create(const dsabf_config *cfg, dsabf_handle **out)
     ck(cudaMalloc(&h->d_ded, slots * cpb * cfg->n_beams * sizeof(float)), "alloc dm0 ring");
     const size_t wbytes = (size_t)cfg->n_channels * cfg->n_antennas * cfg->n_beams * 2;
     ck(cudaMalloc(&h->d_w, wbytes), "alloc weights");
-    ck(cudaMalloc(&h->d_wprep, wbytes), "alloc tensor-core weights");
+    ck(cudaMalloc(&h->d_wprep, 2 * wbytes), "alloc tensor-core weights");   // realified: 2 rows of 2*n_ant bytes per beam
     ck(cudaMalloc(&h->d_bad, sizeof(int)), "alloc flag");
     if (!rc) {
         ck(cudaMemset(h->d_ring, 0, slots * h->block_bytes), "memset ring");           // beamformer.cu:291-298

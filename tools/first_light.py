@@ -54,6 +54,8 @@ def check(name, debug, n_chan, n_chunks, n_beams=256, seed=0, exact=1, **kw):
 
 def timing():
     import torch
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
     B = bf.Beamformer(debug=False)
     rng = np.random.default_rng(1)
     w = rng.integers(-127, 128, size=(256, 64, 256, 2), dtype=np.int8)
@@ -103,6 +105,9 @@ def timing():
 
 
 if __name__ == "__main__":
+    if "--time-only" in sys.argv:
+        timing()
+        sys.exit(0)
     allok = True
     allok &= check("tiny-obs", False, 2, 1, seed=1)
     allok &= check("tiny-dbg", True, 3, 32, seed=2)
