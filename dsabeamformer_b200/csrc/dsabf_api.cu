@@ -173,7 +173,7 @@ int dsabf_create(const dsabf_config *cfg, dsabf_handle **out)
     if (cfg->n_channels < 1) return fail(DSABF_E_INVALID, "n_channels must be >= 1");
     if (cfg->n_pol < 1 || cfg->n_averaging < 1) return fail(DSABF_E_INVALID, "n_pol, n_averaging must be >= 1");
     const int group = cfg->n_pol * cfg->n_averaging;
-    if (!is_pow2(group) || group < 2 || group > 128) return fail(DSABF_E_INVALID, "n_pol*n_averaging must be a power of two in [2,128]");
+    if (!is_pow2(group) || group < 2 || group > 64) return fail(DSABF_E_INVALID, "n_pol*n_averaging must be a power of two in [2,64]");
     const int cpc = cfg->n_outputs_per_chunk * group;
     if (cfg->n_outputs_per_chunk < 1 || !((cpc >= 256 && cpc % 256 == 0) || 256 % cpc == 0))
         return fail(DSABF_E_INVALID, "columns per chunk must divide 256 or be a multiple of 256");

@@ -32,6 +32,7 @@
 // the final float power is written.
 #include "fused_beamform.cuh"
 #include "sm100_ptx.cuh"
+#include <cstddef>
 #include <type_traits>
 
 namespace dsabf {
@@ -40,7 +41,6 @@ using namespace ptx;
 
 namespace {
 
-constexpr int kThreads = 512;
 constexpr int kTileN = 256;              // columns per work item (UMMA N)
 constexpr int kRowBytes = 128;           // K' bytes per row = 2 * 64 antennas
 constexpr int kATileBytes = 128 * kRowBytes;   // 16 KB: one M=128 weights tile
@@ -51,8 +51,13 @@ constexpr int kMaxMT = 4;
 constexpr int kAccCols = 256;            // TMEM columns per accumulator stage
 constexpr int kTmemCols = 512;
 
-constexpr int kEpiWarp0 = 4, kNumEpiWarps = 8;
-constexpr int kUnpackWarp0 = 12, kNumUnpackWarps = 4;
+// warp roles: warpgroup 0 = {TMA, MMA, weights+TMEM alloc, idle}, warpgroup 1 = unpack,
+// warpgroups 2-5 = epilogue (16 warps: TMEM lane quarter = warp % 4, 64 columns each)
+constexpr int kUnpackWarp0 = 4, kNumUnpackWarps = 4;
+constexpr int kEpiWarp0 = 8, kNumEpiWarps = 16;
+constexpr int kThreads = (kEpiWarp0 + kNumEpiWarps) * 32;   // 768
+constexpr int kEpiCols = kTileN / (kNumEpiWarps / 4);       // 64 columns per epilogue warp
+constexpr int kRegsLight = 40, kRegsEpi = 96;               // setmaxnreg budgets (launch: 80)
 
 struct __align__(1024) Smem {
     uint8_t a[kMaxMT][kATileBytes];      // 64 KB  resident weights of the current channel
@@ -65,17 +70,52 @@ struct __align__(1024) Smem {
     uint32_t tmem_base;
 };
 
-// square-accumulate in the two supported arithmetic modes
+// Square-accumulate of one row's voltages in the two supported arithmetic modes.
+// Both keep several independent partial sums so that consecutive columns do not
+// form one long dependent chain.
+//  EXACT : int64 via mad.wide.s32 (IMAD.WIDE) -- integer power exact, slower.
+//  fast  : fp32; two columns at a time are converted (I2FP) and fed to one packed
+//          fma.rn.f32x2 (FFMA2).  Exact whenever the integer power is < 2^24
+//          (every partial sum is then an exactly representable integer multiple
+//          of 256); otherwise <= G * 2^-24 relative, ~1e-7 typical.
 template <bool EXACT> struct Acc;
 template <> struct Acc<true> {
-    long long s;
-    __device__ __forceinline__ void zero() { s = 0; }
-    __device__ __forceinline__ void add(int v) { asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s) : "r"(v)); }
+    using sum_t = long long;
+    long long s0, s1, s2, s3;
+    __device__ __forceinline__ void zero() { s0 = s1 = s2 = s3 = 0; }
+    template <int SLOT> __device__ __forceinline__ void add2(int v0, int v1)
+    {
+        if (SLOT == 0) {
+            asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s0) : "r"(v0));
+            asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s1) : "r"(v1));
+        } else {
+            asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s2) : "r"(v0));
+            asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s3) : "r"(v1));
+        }
+    }
+    // sum of the first NSLOT packed slots that were used since zero()
+    template <int NSLOT> __device__ __forceinline__ long long sum() const { return NSLOT == 1 ? (s0 + s1) : (s0 + s1) + (s2 + s3); }
 };
 template <> struct Acc<false> {
-    float s;
-    __device__ __forceinline__ void zero() { s = 0.f; }
-    __device__ __forceinline__ void add(int v) { float f = __int2float_rn(v); s = fmaf(f, f, s); }
+    using sum_t = float;
+    unsigned long long a0, a1;     // two packed float2 accumulators
+    __device__ __forceinline__ void zero() { a0 = 0ull; a1 = 0ull; }
+    template <int SLOT> __device__ __forceinline__ void add2(int v0, int v1)
+    {
+        float f0, f1;
+        asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f0) : "r"(v0));
+        asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f1) : "r"(v1));
+        if (SLOT == 0) asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a0) : "f"(f0), "f"(f1));
+        else           asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a1) : "f"(f0), "f"(f1));
+    }
+    template <int NSLOT> __device__ __forceinline__ float sum() const
+    {
+        float a, b, c, d;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(a0));
+        if (NSLOT == 1) return a + b;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(c), "=f"(d) : "l"(a1));
+        return (a + b) + (c + d);
+    }
 };
 
 // Work-item geometry shared by all roles.
@@ -88,73 +128,79 @@ struct Geom {
 
 // Per-(row, M-tile) epilogue state of one thread.
 template <bool EXACT> struct EpiCtx {
-    using sum_t = typename std::conditional<EXACT, long long, float>::type;
+    using sum_t = typename Acc<EXACT>::sum_t;
     Acc<EXACT> acc;       // running sum of squares of the current group of G columns
     sum_t pend;           // finished even group waiting for the odd group of its pair
-    int colbase;          // global column of this warp's first TMEM column
-    int n_cols_total;
     int lane_odd;         // odd lanes hold im rows
-    size_t out_base, out_tstride;
-    int32_t *vd;          // voltage dump base for this row (nullptr = off)
-    size_t vd_cstride;
+    int vg_lane;          // (valid groups of this warp's 64 columns) - lane_odd   (ragged last tile)
+    float *op;            // running pointer: &out[next group pair + lane_odd][f][beam of this row]
+    long long *pp;        // same for the exact-power dump (nullptr = off)
+    size_t pair_stride;   // elements between consecutive group pairs = 2 output times
+    float scale;
 };
 
-template <int G, bool EXACT>
-__device__ __forceinline__ void epi_store(const EpiCtx<EXACT> &c, const FusedParams &p, typename EpiCtx<EXACT>::sum_t tot, int col)
+// Store the finished output of group pair PAIR (compile-time) and advance the pointers.
+template <bool EXACT>
+__device__ __forceinline__ void epi_store(EpiCtx<EXACT> &c, typename EpiCtx<EXACT>::sum_t tot, int first_grp_of_pair)
 {
-    if (col < c.n_cols_total) {
-        const size_t o = c.out_base + (size_t)(col / G) * c.out_tstride;
-        p.out[o] = (float)tot * p.scale;
+    if (first_grp_of_pair < c.vg_lane) {
+        *c.op = (float)tot * c.scale;
         if (EXACT) {
-            if (p.pdump) p.pdump[o] = (long long)tot >> 8;
+            if (c.pp) *c.pp = (long long)tot >> 8;
         }
+    }
+    c.op += c.pair_stride;
+    if (EXACT) {
+        if (c.pp) c.pp += c.pair_stride;
     }
 }
 
-// 32 accumulator columns [BLK*32, BLK*32+32) of this warp's 128: square, sum per
+// 32 accumulator columns [BLK*32, BLK*32+32) of this warp's 64: square, sum per
 // group of G columns, and on every second finished group exchange with the lane
 // holding the other component (re rows = even lanes, im rows = odd lanes): even
 // lanes finish the even group of the pair, odd lanes the odd group, so one
 // shuffle yields two outputs and a warp stores 2 x 64 contiguous bytes.
 template <int G, bool EXACT, int BLK>
-__device__ __forceinline__ void epi_block(EpiCtx<EXACT> &c, const FusedParams &p, const uint32_t (&v)[32])
+__device__ __forceinline__ void epi_block(EpiCtx<EXACT> &c, const uint32_t (&v)[32])
 {
-    if (c.vd != nullptr) {
+    constexpr int kGroups = kEpiCols / G;                 // groups per warp: 32,16,8,4,2,1
+    constexpr int kSlots = (G >= 4) ? 2 : 1;              // packed accumulator slots in use
 #pragma unroll
-        for (int jj = 0; jj < 32; jj++) {
-            const int col = c.colbase + BLK * 32 + jj;
-            if (col < c.n_cols_total) c.vd[(size_t)col * c.vd_cstride] = ((int)v[jj]) >> 4;
-        }
-    }
-    constexpr int kGroups = 128 / G;
-#pragma unroll
-    for (int jj = 0; jj < 32; jj++) {
-        c.acc.add((int)v[jj]);
-        const int cl = BLK * 32 + jj;              // compile-time after unrolling
+    for (int jj = 0; jj < 32; jj += 2) {
+        if (kSlots == 1 || ((jj >> 1) & 1) == 0) c.acc.template add2<0>((int)v[jj], (int)v[jj + 1]);
+        else                                     c.acc.template add2<1>((int)v[jj], (int)v[jj + 1]);
+        const int cl = BLK * 32 + jj + 1;          // last column handled so far (compile-time after unrolling)
         if (((cl + 1) % G) == 0) {
             const int grp = cl / G;
-            const auto sgrp = c.acc.s;
+            const auto sgrp = c.acc.template sum<kSlots>();
             c.acc.zero();
             if (kGroups == 1) {
                 const auto tot = sgrp + __shfl_xor_sync(0xffffffffu, sgrp, 1);
-                if (!c.lane_odd) epi_store<G, EXACT>(c, p, tot, c.colbase + cl);
+                // single group: only the even lanes (vg_lane = valid - 0) store
+                if (!c.lane_odd) epi_store<EXACT>(c, tot, 0);
             } else if ((grp & 1) == 0) {
                 c.pend = sgrp;
             } else {
                 const auto send = c.lane_odd ? c.pend : sgrp;
                 const auto mine = c.lane_odd ? sgrp : c.pend;
                 const auto tot = mine + __shfl_xor_sync(0xffffffffu, send, 1);
-                epi_store<G, EXACT>(c, p, tot, c.colbase + cl - (c.lane_odd ? 0 : G));
+                epi_store<EXACT>(c, tot, grp - 1);
             }
         }
     }
 }
 
-template <int G, bool EXACT>
+// MODE: 0 = fast fp32 power, 1 = exact int64 power (+ optional integer-power dump),
+//       2 = exact + int32 voltage dump (debug / parity tap)
+template <int G, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const FusedParams p)
 {
+    constexpr bool EXACT = MODE != 0;
+    constexpr bool DUMP = MODE == 2;
     extern __shared__ uint8_t smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align in the shared address space (keeps every later address a cheap 32-bit add)
+    uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw + (sbase - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -180,37 +226,44 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
+    // 32-bit shared addresses, computed once (opaque so that they are not rematerialised in the loops)
+    asm volatile("" : "+r"(sbase));
+    const uint32_t a_smem = sbase + (uint32_t)offsetof(Smem, a), b_smem = sbase + (uint32_t)offsetof(Smem, b),
+                   stg_smem = sbase + (uint32_t)offsetof(Smem, stg);
+    const uint32_t bar_stg_full = sbase + (uint32_t)offsetof(Smem, stg_full), bar_stg_empty = sbase + (uint32_t)offsetof(Smem, stg_empty);
+    const uint32_t bar_b_full = sbase + (uint32_t)offsetof(Smem, b_full), bar_b_empty = sbase + (uint32_t)offsetof(Smem, b_empty);
+    const uint32_t bar_a_full = sbase + (uint32_t)offsetof(Smem, a_full), bar_a_empty = sbase + (uint32_t)offsetof(Smem, a_empty);
+    const uint32_t bar_acc_full = sbase + (uint32_t)offsetof(Smem, acc_full), bar_acc_empty = sbase + (uint32_t)offsetof(Smem, acc_empty);
 
-    if (warp == 0) {
-        // ================= TMA producer: packed voltages =================
-        if (lane == 0) {
+    if (warp < kUnpackWarp0) {
+        setmaxnreg_dec<kRegsLight>();
+        if (warp == 0 && lane == 0) {
+            // ================= TMA producer: packed voltages =================
             const uint64_t pol = policy_evict_first();
             for (int item = item_begin, it = 0; item < item_end; item++, it++) {
                 const int f = item / g.n_tiles, t = item - f * g.n_tiles;
                 const int s = it % kStages;
-                mbar_wait(&sm.stg_empty[s], ((it / kStages) & 1) ^ 1, 1);
+                mbar_wait(bar_stg_empty + 8 * s, ((it / kStages) & 1) ^ 1, 1);
                 const int col0 = t * kTileN;
                 if (g.cpc >= kTileN) {
                     const int chunk = col0 / g.cpc, c_in = col0 - chunk * g.cpc;
                     const uint8_t *src = p.packed + (((size_t)chunk * g.n_chan + f) * g.cpc + c_in) * 64;
-                    mbar_arrive_expect_tx(&sm.stg_full[s], kStageBytes);
-                    tma_bulk_g2s_hint(sm.stg[s], src, kStageBytes, &sm.stg_full[s], pol);
+                    mbar_arrive_expect_tx(bar_stg_full + 8 * s, kStageBytes);
+                    tma_bulk_g2s_hint(stg_smem + s * kStageBytes, src, kStageBytes, bar_stg_full + 8 * s, pol);
                 } else {
                     const int per_tile = kTileN / g.cpc;
                     const int chunk0 = t * per_tile;
                     const int nseg = min(per_tile, g.n_chunks - chunk0);
                     const uint32_t seg_bytes = g.cpc * 64;
-                    mbar_arrive_expect_tx(&sm.stg_full[s], seg_bytes * nseg);
+                    mbar_arrive_expect_tx(bar_stg_full + 8 * s, seg_bytes * nseg);
                     for (int k = 0; k < nseg; k++) {
                         const uint8_t *src = p.packed + (((size_t)(chunk0 + k) * g.n_chan + f) * g.cpc) * 64;
-                        tma_bulk_g2s_hint(sm.stg[s] + k * seg_bytes, src, seg_bytes, &sm.stg_full[s], pol);
+                        tma_bulk_g2s_hint(stg_smem + s * kStageBytes + k * seg_bytes, src, seg_bytes, bar_stg_full + 8 * s, pol);
                     }
                 }
             }
-        }
-    } else if (warp == 2) {
-        // ================= weights loader =================
-        if (lane == 0) {
+        } else if (warp == 2 && lane == 0) {
+            // ================= weights loader =================
             const uint64_t pol = policy_evict_last();
             int cur_f = -1, ch = 0;
             for (int item = item_begin; item < item_end; item++) {
@@ -218,16 +271,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 if (f == cur_f) continue;
                 cur_f = f;
                 for (int m = 0; m < mt; m++) {
-                    mbar_wait(&sm.a_empty[m], (ch & 1) ^ 1, 2);
-                    mbar_arrive_expect_tx(&sm.a_full[m], kATileBytes);
-                    tma_bulk_g2s_hint(sm.a[m], p.wprep + ((size_t)f * mt + m) * kATileBytes, kATileBytes, &sm.a_full[m], pol);
+                    mbar_wait(bar_a_empty + 8 * m, (ch & 1) ^ 1, 2);
+                    mbar_arrive_expect_tx(bar_a_full + 8 * m, kATileBytes);
+                    tma_bulk_g2s_hint(a_smem + m * kATileBytes, p.wprep + ((size_t)f * mt + m) * kATileBytes, kATileBytes, bar_a_full + 8 * m, pol);
                 }
                 ch++;
             }
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        } else if (warp == 1 && lane == 0) {
+            // ================= MMA issuer =================
             constexpr uint32_t idesc = make_idesc_i8(128, kTileN);
             int cur_f = -1, ch = -1;
             uint32_t acc_cnt = 0;
@@ -237,28 +288,29 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 if (new_ch) { cur_f = f; ch++; }
                 const bool last_of_ch = (item + 1 == item_end) || ((item + 1) / g.n_tiles != f);
                 const int buf = it & 1;
-                mbar_wait(&sm.b_full[buf], (it >> 1) & 1, 3);
+                mbar_wait(bar_b_full + 8 * buf, (it >> 1) & 1, 3);
                 tc_fence_after();
-                const uint64_t bdesc = make_desc_k_sw128(smem_u32(sm.b[buf]));
+                const uint64_t bdesc = make_desc_k_sw128(b_smem + buf * kBTileBytes);
                 for (int m = 0; m < mt; m++) {
-                    if (new_ch) mbar_wait(&sm.a_full[m], ch & 1, 4);
+                    if (new_ch) mbar_wait(bar_a_full + 8 * m, ch & 1, 4);
                     const uint32_t as = acc_cnt & 1;
-                    mbar_wait(&sm.acc_empty[as], ((acc_cnt >> 1) & 1) ^ 1, 5);
+                    mbar_wait(bar_acc_empty + 8 * as, ((acc_cnt >> 1) & 1) ^ 1, 5);
                     tc_fence_after();
-                    const uint64_t adesc = make_desc_k_sw128(smem_u32(sm.a[m]));
+                    const uint64_t adesc = make_desc_k_sw128(a_smem + m * kATileBytes);
                     const uint32_t d = tmem_base + as * kAccCols;
 #pragma unroll
                     for (int k = 0; k < kRowBytes / 32; k++)   // K = 32 bytes per instruction; +32 B = +2 in the descriptor
                         mma_i8_ss(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0);
-                    tc_commit(&sm.acc_full[as]);
-                    if (last_of_ch) tc_commit(&sm.a_empty[m]);
+                    tc_commit(bar_acc_full + 8 * as);
+                    if (last_of_ch) tc_commit(bar_a_empty + 8 * m);
                     acc_cnt++;
                 }
-                tc_commit(&sm.b_empty[buf]);
+                tc_commit(bar_b_empty + 8 * buf);
             }
         }
-    } else if (warp >= kUnpackWarp0) {
+    } else if (warp < kEpiWarp0) {
         // ================= unpack: 4-bit+4-bit -> int8 (x16), into SW128 K-major B' =================
+        setmaxnreg_dec<kRegsLight>();
         const int uw = warp - kUnpackWarp0;
         // lane -> (row r in an 8-column group, 16-byte antenna chunk c): chosen so that both the
         // 16 B loads (64 B rows) and the swizzled 16 B stores (128 B rows) are bank-conflict free.
@@ -269,10 +321,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
         const uint32_t st_im = r * 128 + (((c + 4) ^ r) << 4);
         for (int item = item_begin, it = 0; item < item_end; item++, it++) {
             const int s = it % kStages, buf = it & 1;
-            mbar_wait(&sm.stg_full[s], (it / kStages) & 1, 6);
-            mbar_wait(&sm.b_empty[buf], ((it >> 1) & 1) ^ 1, 7);
-            const uint32_t src = smem_u32(sm.stg[s]) + ld_off;
-            const uint32_t dst = smem_u32(sm.b[buf]);
+            mbar_wait(bar_stg_full + 8 * s, (it / kStages) & 1, 6);
+            mbar_wait(bar_b_empty + 8 * buf, ((it >> 1) & 1) ^ 1, 7);
+            const uint32_t src = stg_smem + s * kStageBytes + ld_off;
+            const uint32_t dst = b_smem + buf * kBTileBytes;
 #pragma unroll
             for (int i = 0; i < (kTileN / 8) / kNumUnpackWarps; i++) {
                 const int grp = uw + i * kNumUnpackWarps;      // 8-column group
@@ -287,54 +339,69 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&sm.b_full[buf]); mbar_arrive(&sm.stg_empty[s]); }
+            if (lane == 0) { mbar_arrive(bar_b_full + 8 * buf); mbar_arrive(bar_stg_empty + 8 * s); }
         }
-    } else if (warp >= kEpiWarp0) {
+    } else {
         // ================= epilogue: TMEM -> |V|^2 summed over G columns -> float power =================
+        setmaxnreg_inc<kRegsEpi>();
         const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                  // which 128 columns of the tile
+        const int wc = ew >> 2;                    // which 64 columns of the tile
         const int row = quarter * 32 + lane;       // A' row: beam = row/2, component = row&1
-        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        uint32_t tbase_w = tmem_base + ((uint32_t)(quarter * 32) << 16) + wc * kEpiCols;
+        asm volatile("" : "+r"(tbase_w));
+        constexpr int kGroups = kEpiCols / G;
+        EpiCtx<EXACT> ctx;
+        ctx.lane_odd = lane & 1;
+        const size_t tstride = (size_t)g.n_chan * p.n_beams;      // floats between consecutive output times
+        ctx.pair_stride = 2 * tstride;
+        ctx.scale = p.scale;
         uint32_t acc_cnt = 0;
+#pragma unroll 1
         for (int item = item_begin; item < item_end; item++) {
             const int f = item / g.n_tiles, t = item - f * g.n_tiles;
-            const int colbase = t * kTileN + half * 128;    // first global column of this warp's half
+            const int colbase = t * kTileN + wc * kEpiCols;          // first global column of this warp
+            const int cols_left = g.n_cols_total - colbase;
+            ctx.vg_lane = (cols_left >= kEpiCols ? kGroups : (cols_left > 0 ? cols_left / G : 0)) - ctx.lane_odd;
+            // even lanes (re rows) store the even group of each pair, odd lanes the odd group
+            const size_t out_off = ((size_t)(colbase / G) + ((kGroups > 1) ? ctx.lane_odd : 0)) * tstride + (size_t)f * p.n_beams + (row >> 1);
+            float *out_item = p.out + out_off;
+            asm volatile("" : "+l"(out_item));                       // keep the pointer live; do not recompute per M-tile
+            long long *pp_item = (EXACT && p.pdump) ? p.pdump + out_off : nullptr;
+#pragma unroll 1
             for (int m = 0; m < mt; m++, acc_cnt++) {
                 const uint32_t as = acc_cnt & 1;
-                mbar_wait(&sm.acc_full[as], (acc_cnt >> 1) & 1, 8);
+                mbar_wait(bar_acc_full + 8 * as, (acc_cnt >> 1) & 1, 8);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + lane_addr + as * kAccCols + half * 128;
-                const int beam0 = m * 64;
-
-                EpiCtx<EXACT> ctx;
-                ctx.acc.zero();
-                ctx.pend = 0;
-                ctx.colbase = colbase;
-                ctx.n_cols_total = g.n_cols_total;
-                ctx.lane_odd = lane & 1;
-                // out index of (output time 0, channel f, this row's beam); one output time = n_chan*n_beams floats
-                ctx.out_base = (size_t)f * p.n_beams + beam0 + (row >> 1);
-                ctx.out_tstride = (size_t)g.n_chan * p.n_beams;
-                ctx.vd = p.vdump ? p.vdump + ((size_t)f * g.n_cols_total * p.n_beams + beam0) * 2 + row : nullptr;
-                ctx.vd_cstride = (size_t)p.n_beams * 2;
+                const uint32_t taddr = tbase_w + as * kAccCols;
                 uint32_t va[32], vb[32];
                 tmem_ld_32x32(taddr, va);
-                tmem_ld_wait(va);
                 tmem_ld_32x32(taddr + 32, vb);
-                epi_block<G, EXACT, 0>(ctx, p, va);
-                tmem_ld_wait(vb);
-                tmem_ld_32x32(taddr + 64, va);
-                epi_block<G, EXACT, 1>(ctx, p, vb);
                 tmem_ld_wait(va);
-                tmem_ld_32x32(taddr + 96, vb);
-                epi_block<G, EXACT, 2>(ctx, p, va);
                 tmem_ld_wait(vb);
-                // all of this warp's TMEM reads of the stage are done: hand it back to the MMA
+                // both halves are in registers: hand the TMEM stage back to the MMA right away
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.acc_empty[as]);
-                epi_block<G, EXACT, 3>(ctx, p, vb);
+                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+
+                if (DUMP) {
+                    // debug tap: int32 voltages, [f][col][beam][2]; this thread's (beam, component) = row
+                    int32_t *vd = p.vdump + ((size_t)f * g.n_cols_total * p.n_beams + m * 64) * 2 + row;
+                    const size_t cs = (size_t)p.n_beams * 2;
+#pragma unroll
+                    for (int jj = 0; jj < 32; jj++) {
+                        if (colbase + jj < g.n_cols_total) vd[(size_t)(colbase + jj) * cs] = ((int)va[jj]) >> 4;
+                        if (colbase + 32 + jj < g.n_cols_total) vd[(size_t)(colbase + 32 + jj) * cs] = ((int)vb[jj]) >> 4;
+                    }
+                }
+                ctx.acc.zero();
+                ctx.pend = 0;
+                ctx.op = out_item;
+                ctx.pp = pp_item;
+                epi_block<G, EXACT, 0>(ctx, va);
+                epi_block<G, EXACT, 1>(ctx, vb);
+                out_item += 64;                                      // next M-tile = next 64 beams
+                if (EXACT) { if (pp_item) pp_item += 64; }
             }
         }
     }
@@ -345,31 +412,30 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
     if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <int G, bool EXACT>
+template <int G, int MODE>
 cudaError_t launch_one(const FusedParams &p, int grid, cudaStream_t stream)
 {
     const size_t smem = sizeof(Smem) + 1024;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_beamform_kernel<G, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fused_beamform_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    fused_beamform_kernel<G, EXACT><<<grid, kThreads, smem, stream>>>(p);
+    fused_beamform_kernel<G, MODE><<<grid, kThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-template <bool EXACT>
+template <int MODE>
 cudaError_t launch_g(const FusedParams &p, int grid, cudaStream_t stream)
 {
     switch (p.group) {
-    case 2: return launch_one<2, EXACT>(p, grid, stream);
-    case 4: return launch_one<4, EXACT>(p, grid, stream);
-    case 8: return launch_one<8, EXACT>(p, grid, stream);
-    case 16: return launch_one<16, EXACT>(p, grid, stream);
-    case 32: return launch_one<32, EXACT>(p, grid, stream);
-    case 64: return launch_one<64, EXACT>(p, grid, stream);
-    case 128: return launch_one<128, EXACT>(p, grid, stream);
+    case 2: return launch_one<2, MODE>(p, grid, stream);
+    case 4: return launch_one<4, MODE>(p, grid, stream);
+    case 8: return launch_one<8, MODE>(p, grid, stream);
+    case 16: return launch_one<16, MODE>(p, grid, stream);
+    case 32: return launch_one<32, MODE>(p, grid, stream);
+    case 64: return launch_one<64, MODE>(p, grid, stream);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -385,7 +451,8 @@ cudaError_t launch_fused_beamform(const FusedParams &p, bool exact, int num_sms,
     const long long items = (long long)p.n_chan * p.n_tiles;
     if (items <= 0) return cudaSuccess;
     const int grid = (int)(items < num_sms ? items : num_sms);
-    return exact ? launch_g<true>(p, grid, stream) : launch_g<false>(p, grid, stream);
+    if (p.vdump) return launch_g<2>(p, grid, stream);
+    return exact ? launch_g<1>(p, grid, stream) : launch_g<0>(p, grid, stream);
 }
 
 // ---------------------------------------------------------------------------

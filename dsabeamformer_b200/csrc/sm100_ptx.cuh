@@ -30,35 +30,52 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase
+// completes or the hint (ns) expires, so waiting warps do not burn issue slots.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.b32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU.
+// The clock is only consulted every 256 failed probes.
 #ifndef DSABF_WAIT_TIMEOUT_CYCLES
-#define DSABF_WAIT_TIMEOUT_CYCLES (6000000000LL)
+#define DSABF_WAIT_TIMEOUT_CYCLES (8000000000LL)
 #endif
-__device__ __noinline__ void mbar_timeout(int tag, uint32_t parity)
+// NOTE: no printf here by default -- a device-side call anywhere in the kernel makes
+// ptxas apply the smallest setmaxnreg budget to the whole kernel (measured: the
+// epilogue spilled its TMEM registers to local memory).  -DDSABF_DEBUG_WAIT brings
+// the message back for debugging.
+__device__ __forceinline__ void mbar_timeout(int tag, uint32_t parity)
 {
+#ifdef DSABF_DEBUG_WAIT
     printf("dsabf: mbarrier wait timeout (tag %d, block %d, thread %d, parity %u)\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
+#else
+    (void)tag;
+    (void)parity;
+#endif
     __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag = 0)
 {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    long long t0 = 0;
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > DSABF_WAIT_TIMEOUT_CYCLES) mbar_timeout(tag, parity);
+        if ((++spins & 255u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > DSABF_WAIT_TIMEOUT_CYCLES) mbar_timeout(tag, parity);
+        }
     }
 }
 
@@ -188,6 +205,60 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32])
                  :
                  : "memory");
 }
+
+
+// ---- the same operations on precomputed 32-bit shared-memory addresses (hot loops:
+// the generic->shared conversion is otherwise redone at every use) ----
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = 0;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 255u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > DSABF_WAIT_TIMEOUT_CYCLES) mbar_timeout(tag, parity);
+        }
+    }
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(uint32_t smem_dst, const void *gmem_src, uint32_t bytes, uint32_t bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_dst),
+        "l"(gmem_src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// register re-budgeting between warp roles (whole warpgroups of 4 warps)
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr)
 {

@@ -48,7 +48,7 @@ typedef struct dsabf_config {
     int n_beams;              /* N_BEAMS 256   (multiple of 64, <= 256)                      */
     int n_channels;           /* N_FREQUENCIES 256 (any >= 1)                                */
     int n_pol;                /* N_POL 2                                                     */
-    int n_averaging;          /* N_AVERAGING: 16 observation / 1 DEBUG (power of two <= 64) */
+    int n_averaging;          /* N_AVERAGING: 16 observation / 1 DEBUG (power of two <= 32) */
     int n_outputs_per_chunk;  /* N_OUTPUTS_PER_GEMM 8                                        */
     int n_chunks_per_block;   /* N_GEMMS_PER_BLOCK 32                                        */
     int n_ring_slots;         /* N_BLOCKS_ON_GPU 8: device ring of input blocks              */

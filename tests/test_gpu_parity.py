@@ -1,0 +1,286 @@
+"""GPU (-m gpu): parity of the sm_100a path, called through the C ABI, against the
+oracle on identical seeded inputs; against the reference's own kernels + cuBLAS
+replayed on the box (oracle/_ref/ref_kernels_*); and size-independent properties
+at BASELINE.json's full sizes.
+
+Bars (BASELINE.json north_star): int32 beam voltages bit-exact; integer power
+bit-exact; float power bit-exact where the integer power is < 2^24, otherwise
+within 1e-6 relative of the reference's float path.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-6          # north_star tolerance for float power
+ALPHA2 = float(np.float32(1.0 / 127)) ** 2
+
+
+def _rand_case(bf, debug, n_chan, n_chunks, seed, n_beams=256, int4_full_range=True, **kw):
+    rng = np.random.default_rng(seed)
+    B = bf.Beamformer(debug=debug, n_channels=n_chan, n_beams=n_beams, **kw)
+    w = rng.integers(-127, 128, size=(n_chan, 64, n_beams, 2), dtype=np.int8)
+    B.set_weights(w)
+    packed = rng.integers(0, 256, size=(n_chunks, n_chan, B.cols_per_chunk, 64), dtype=np.uint8)
+    return B, w, packed
+
+
+def _check_against_oracle(O, B, w, packed, float_out):
+    cols, G = B.cols_per_chunk, B.group
+    n_out = cols // G
+    V, P = B.voltages(packed)
+    for c in range(packed.shape[0]):
+        Vo = O.beamform(packed[c], w)
+        assert np.array_equal(V[:, c * cols:(c + 1) * cols], Vo), "int32 voltages differ (chunk %d)" % c
+        Po = O.power_int(Vo, G)
+        assert np.array_equal(P[c * n_out:(c + 1) * n_out], Po), "int64 power differs (chunk %d)" % c
+        Fo = O.detect_ref_float(Vo, G)
+        Fg = float_out[c * n_out:(c + 1) * n_out]
+        rel = np.abs(Fg.astype(np.float64) - Fo) / np.maximum(Fo, 1e-30)
+        assert rel.max() <= REL_TOL, "float power off by %.3e (chunk %d)" % (rel.max(), c)
+
+
+@pytest.mark.parametrize("exact", [0, 1])
+@pytest.mark.parametrize("debug,n_chan,n_chunks", [(False, 3, 2), (True, 5, 32), (True, 2, 21), (False, 160, 1)])
+def test_random_inputs_match_oracle(bf, oracle, debug, n_chan, n_chunks, exact):
+    """all 256 byte values (nibble -8 included), weights in [-127,127]; ragged tile (21 chunks of
+    16 columns = 336 columns = 1.3 tiles); more channels than SMs (160 > 148)."""
+    B, w, packed = _rand_case(bf, debug, n_chan, n_chunks, seed=100 + n_chan, exact_power=exact)
+    _check_against_oracle(oracle, B, w, packed, B.beamform(packed))
+    B.close()
+
+
+@pytest.mark.parametrize("n_beams", [64, 128, 192])
+def test_fewer_beams(bf, oracle, n_beams):
+    B, w, packed = _rand_case(bf, False, 2, 1, seed=7, n_beams=n_beams)
+    _check_against_oracle(oracle, B, w, packed, B.beamform(packed))
+    B.close()
+
+
+@pytest.mark.parametrize("navg", [2, 4, 8, 32])
+def test_other_averaging_lengths(bf, oracle, navg):
+    B, w, packed = _rand_case(bf, False, 2, 2 if navg < 32 else 1, seed=navg, n_averaging=navg)
+    _check_against_oracle(oracle, B, w, packed, B.beamform(packed))
+    B.close()
+
+
+def test_extreme_values_worst_case_voltage(bf, oracle):
+    """every sample -8-8j, every weight +-127: |V| reaches the 64*127*8*2 = 130 048 bound."""
+    B = bf.Beamformer(debug=False, n_channels=2)
+    w = np.full((2, 64, 256, 2), 127, dtype=np.int8)
+    w[1, :, ::2, 1] = -127
+    B.set_weights(w)
+    packed = np.full((1, 2, 256, 64), 0x88, dtype=np.uint8)
+    V, P = B.voltages(packed)
+    Vo = oracle.beamform(packed[0], w)
+    assert np.array_equal(V, Vo) and np.abs(Vo).max() == 130048
+    assert np.array_equal(P, oracle.power_int(Vo, 32))
+    B.close()
+
+
+def test_weight_minus_128_is_rejected(bf):
+    B = bf.Beamformer(debug=True, n_channels=1)
+    w = np.zeros((1, 64, 256, 2), dtype=np.int8)
+    w[0, 3, 5, 1] = -128
+    with pytest.raises(bf.DsabfError) as e:
+        B.set_weights(w)
+    assert e.value.code == bf.E_WEIGHT
+    with pytest.raises(bf.DsabfError):       # and the handle refuses to compute without weights
+        B.beamform(np.zeros((1, 1, 16, 64), dtype=np.uint8))
+    B.close()
+
+
+def test_empty_and_zero_inputs(bf):
+    B = bf.Beamformer(debug=True, n_channels=2)
+    B.set_weights(np.ones((2, 64, 256, 2), dtype=np.int8))
+    assert B.beamform(np.zeros((0, 2, 16, 64), dtype=np.uint8)).shape == (0, 2, 256)
+    out = B.beamform(np.zeros((3, 2, 16, 64), dtype=np.uint8))
+    assert out.shape == (24, 2, 256) and not out.any()
+    B.close()
+
+
+def test_bit_exact_below_2_24(bf, oracle):
+    """small signals: integer power < 2^24 => float power must equal the integer exactly
+    (power_scale = 1 returns the raw integer power as float)."""
+    rng = np.random.default_rng(3)
+    B = bf.Beamformer(debug=True, n_channels=4, exact_power=0, power_scale=1.0)
+    w = rng.integers(-12, 13, size=(4, 64, 256, 2), dtype=np.int8)
+    B.set_weights(w)
+    nib = rng.integers(-2, 3, size=(4, 4, 16, 64, 2))
+    packed = (((nib[..., 0] & 0xF) << 4) | (nib[..., 1] & 0xF)).astype(np.uint8)
+    out = B.beamform(packed)
+    for c in range(4):
+        Po = oracle.power_int(oracle.beamform(packed[c], w), 2)
+        assert Po.max() < 2 ** 24
+        assert np.array_equal(out[c * 8:(c + 1) * 8].astype(np.int64), Po)
+        assert np.array_equal(out[c * 8:(c + 1) * 8], Po.astype(np.float32))
+    B.close()
+
+
+@pytest.mark.parametrize("shape,cfg", [("dbg", ("linear_positions.txt", "linear_directions.txt", "linear_source_directions_1024.txt")),
+                                       ("obs", ("grid_positions.txt", "grid_beam_directions.txt", "grid_source_directions_4096.txt"))])
+def test_against_reference_kernels_on_this_gpu(bf, oracle, config_dir, tmp_path, shape, cfg):
+    """The reference's expand_input + cublasGemmStridedBatchedEx + detect_sum (+ gemv) rebuilt for
+    sm_100, run here on the same bytes: V == lrintf(127*C) bit-exact, power within 1e-6, DM-0 sums
+    within 256*2^-24 (cuBLAS gemv order is unspecified)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_kernels_" + shape)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    debug = shape == "dbg"
+    pos = oracle.read_positions(os.path.join(config_dir, cfg[0]))
+    dirs = oracle.read_directions(os.path.join(config_dir, cfg[1]), 256)
+    src = oracle.read_directions(os.path.join(config_dir, cfg[2]))
+    pick = [0, 137, 500, src.shape[0] - 1]
+    w = bf.compute_weights(pos, dirs, 0)
+    cols = 16 if debug else 256
+    data = oracle.generate(pos, src[pick], n_chunks=len(pick), cols=cols)
+    w.tofile(tmp_path / "w.i8")
+    data.tofile(tmp_path / "x.u8")
+    r = subprocess.run([exe, str(tmp_path / "w.i8"), str(tmp_path / "x.u8"), str(len(pick)), str(tmp_path / "ref")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "gemm_status 0" in r.stdout, r.stdout + r.stderr
+    C = np.fromfile(tmp_path / "ref.C.f32", dtype=np.float32).reshape(256, cols, 256, 2)
+    ref_out = np.fromfile(tmp_path / "ref.out.f32", dtype=np.float32).reshape(len(pick) * 8, 256, 256)
+    ref_ded = np.fromfile(tmp_path / "ref.ded.f32", dtype=np.float32).reshape(len(pick), 256)
+
+    B = bf.Beamformer(debug=debug)
+    B.set_weights(w)
+    V, _ = B.voltages(data[:1], want_power=False)
+    assert np.array_equal(V, np.rint(C.astype(np.float64) * 127).astype(np.int32))
+    out = B.beamform(data)
+    rel = np.abs(out.astype(np.float64) - ref_out) / np.maximum(ref_out, 1e-30)
+    assert rel.max() <= REL_TOL
+    # DM-0 through the streaming entry point (the DEBUG gemv path)
+    import torch
+    hin = torch.from_numpy(data.reshape(-1)).pin_memory()
+    hout = torch.empty(len(pick) * B.chunk_out_floats, dtype=torch.float32).pin_memory()
+    hded = torch.empty(len(pick) * 256, dtype=torch.float32).pin_memory()
+    B.enqueue_h2d(0, hin.data_ptr(), hin.numel())
+    t = B.enqueue_block(0, len(pick), hout.data_ptr(), hded.data_ptr(), len(pick))
+    B.sync()
+    assert B.query_analysis(t) == 1
+    assert np.array_equal(hout.numpy().reshape(out.shape), out)
+    ded = hded.numpy().reshape(len(pick), 256)
+    assert (np.abs(ded - ref_ded) <= 256 * 2.0 ** -24 * np.abs(ref_ded) + 1e-30).all()
+    B.close()
+
+
+def test_reference_gpu_fixture(bf, oracle, config_dir):
+    """Committed outputs of the reference's kernels (tests/golden/ref_gpu_fixture.npz, made on a
+    B200 by tools/make_ref_gpu_fixture.py): power subsample + DM-0 rows for 3 linear sources."""
+    path = os.path.join(ROOT, "tests", "golden", "ref_gpu_fixture.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated yet")
+    fx = np.load(path)
+    pos = oracle.read_positions(os.path.join(config_dir, "linear_positions.txt"))
+    dirs = oracle.read_directions(os.path.join(config_dir, "linear_directions.txt"), 256)
+    src = oracle.read_directions(os.path.join(config_dir, "linear_source_directions_1024.txt"))
+    pick = fx["sources"].tolist()
+    for shape, debug in (("dbg", True), ("obs", False)):
+        B = bf.Beamformer(debug=debug)
+        B.set_weights(bf.compute_weights(pos, dirs, 0))
+        data = oracle.generate(pos, src[pick], n_chunks=len(pick), cols=B.cols_per_chunk)
+        out = B.beamform(data)
+        sub = out[:, ::int(fx["chan_step"]), ::int(fx["beam_step"])]
+        rel = np.abs(sub.astype(np.float64) - fx[shape + "_out_sub"]) / np.maximum(fx[shape + "_out_sub"], 1e-30)
+        assert rel.max() <= REL_TOL
+        dm0 = out.reshape(len(pick), 8, 256, 256)[:, 0].astype(np.float64).sum(axis=1)
+        assert (np.abs(dm0 - fx[shape + "_ded"]) <= 2e-5 * np.abs(fx[shape + "_ded"])).all()
+        B.close()
+
+
+# ---------------- full BASELINE sizes: size-independent properties ----------------
+def test_full_block_linearity_and_pol_time_invariance(bf, oracle):
+    """One full observation block (32 chunks x 4 MiB = 128 MiB, 256 ch x 256 beams):
+    (1) V is linear in the weights' sign: negating W leaves the power unchanged bit for bit;
+    (2) permuting the 32 columns inside an averaging group leaves int64 power unchanged;
+    (3) spot rows agree with the oracle."""
+    rng = np.random.default_rng(11)
+    w = rng.integers(-127, 128, size=(256, 64, 256, 2), dtype=np.int8)
+    B = bf.Beamformer(debug=False, exact_power=1, power_scale=1.0)
+    B.set_weights(w)
+    packed = rng.integers(0, 256, size=(32, 256, 256, 64), dtype=np.uint8)
+    out = B.beamform(packed)
+    assert out.shape == (256, 256, 256)
+    perm = packed.reshape(32, 256, 8, 32, 64)[:, :, :, rng.permutation(32)].reshape(packed.shape)
+    out_p = B.beamform(perm)
+    assert np.array_equal(out, out_p)
+    B.set_weights((-w.astype(np.int16)).astype(np.int8))
+    assert np.array_equal(out, B.beamform(packed))
+    B.set_weights(w)
+    for c, f in ((0, 0), (17, 200), (31, 255)):
+        Vo = oracle.beamform(packed[c, f:f + 1], w[f:f + 1])
+        Po = oracle.power_int(Vo, 32)[:, 0]
+        assert np.array_equal(out[c * 8:(c + 1) * 8, f], Po.astype(np.float32))
+    B.close()
+
+
+def test_full_debug_batch_dm0_against_oracle(bf, oracle, config_dir):
+    """Config 1 end to end at full size: 1024 linear sources (256 MiB), DEBUG shape, DM-0 sums
+    data.py-style [source][beam]; every 16th source checked against the oracle's float path."""
+    import torch
+    pos = oracle.read_positions(os.path.join(config_dir, "linear_positions.txt"))
+    dirs = oracle.read_directions(os.path.join(config_dir, "linear_directions.txt"), 256)
+    src = oracle.read_directions(os.path.join(config_dir, "linear_source_directions_1024.txt"))
+    w = bf.compute_weights(pos, dirs, 0)
+    data = oracle.generate(pos, src)
+    B = bf.Beamformer(debug=True)
+    B.set_weights(w)
+    hin = torch.from_numpy(data.reshape(-1)).pin_memory()
+    hded = torch.empty(1024 * 256, dtype=torch.float32).pin_memory()
+    tickets = []
+    for blk in range(32):
+        slot = blk % 8
+        B.enqueue_h2d(slot, hin.data_ptr() + blk * B.block_bytes, B.block_bytes)
+        tickets.append(B.enqueue_block(slot, 32, None, hded.data_ptr() + blk * 32 * 256 * 4, 32))
+    B.sync()
+    assert all(B.query_analysis(t) == 1 for t in tickets)
+    ded = hded.numpy().reshape(1024, 256)
+    for s in range(0, 1024, 16):
+        ref = oracle.dm0(oracle.detect_ref_float(oracle.beamform(data[s], w), 2))
+        assert (np.abs(ded[s] - ref) <= 2e-5 * ref).all(), s
+    # physics sanity of config 1: an off-broadside source is brightest in the beam pointing at it
+    # (near broadside the regular array's grating lobes tie, so sources 0 and 513 are used)
+    assert int(np.argmax(ded[0])) == 0 and int(np.argmax(ded[513])) == 128
+    assert ded.max() > 1e8
+    B.close()
+
+
+def test_dedisperse_matches_oracle(bf, oracle):
+    rng = np.random.default_rng(9)
+    n_t, n_chan, n_beams = 96, 64, 128
+    power = rng.random((n_t, n_chan, n_beams), dtype=np.float32) * 100
+    dms = oracle.dm_trials(300.0, 2048)[::4][:13]
+    freq = 1.53 - np.arange(n_chan) * (0.25 / n_chan)
+    delay = oracle.dm_delays(dms, freq)
+    delay = np.minimum(delay, 60)
+    B = bf.Beamformer(debug=True, n_channels=1)
+    got = B.dedisperse(power, delay, 40)
+    ref = oracle.dedisperse(power, delay, 40)
+    assert np.allclose(got, ref, rtol=2e-6, atol=0)
+    # DM 0 == the DEBUG gemv: plain channel sum
+    assert np.allclose(got[0], power[:40].sum(axis=1), rtol=2e-6)
+    B.close()
+
+
+def test_dedisperse_recovers_injected_pulse(bf, oracle):
+    """sandbox/Dispersion Theory.ipynb cell 5 style: a dispersed pulse peaks at its own DM trial."""
+    n_t, n_chan, n_beams = 400, 256, 64
+    freq = 1.53 - np.arange(n_chan) * (0.25 / n_chan)
+    dms = oracle.dm_trials(600.0, 2048)[::8]
+    delay = oracle.dm_delays(dms, freq)
+    true = len(dms) // 2
+    power = np.ones((n_t, n_chan, n_beams), dtype=np.float32)
+    for f in range(n_chan):
+        power[50 + delay[true, f], f, 5] += 20.0
+    B = bf.Beamformer(debug=True, n_channels=1)
+    n_t_out = n_t - int(delay.max())
+    ded = B.dedisperse(power, delay, n_t_out)
+    peak = np.unravel_index(np.argmax(ded[:, :, 5]), ded[:, :, 5].shape)
+    assert peak == (true, 50)
+    B.close()
