@@ -9,7 +9,7 @@
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
-enum Op { I2FP, IADD3, IMAD, FADD, FADD2, FFMA, FFMA2, LOP3, IMADWIDE, MIX_I2FP_FFMA2, MIX_IMAD_FADD2_FFMA2, MIX_HALF };
+enum Op { FFMA2_DENORM, FFMA_DENORM, I2FP, IADD3, IMAD, FADD, FADD2, FFMA, FFMA2, LOP3, IMADWIDE, MIX_I2FP_FFMA2, MIX_IMAD_FADD2_FFMA2, MIX_HALF };
 
 template <int OP>
 __global__ void __launch_bounds__(1024, 1) k(int iters, const int *in, int *out)
@@ -20,6 +20,12 @@ __global__ void __launch_bounds__(1024, 1) k(int iters, const int *in, int *out)
     for (int j = 0; j < 16; j++) r[j] = in[(threadIdx.x + j) & 1023];
 #pragma unroll
     for (int j = 0; j < 8; j++) q[j] = ((unsigned long long)r[2 * j] << 32) | r[2 * j + 1];
+    if (OP == FFMA2_DENORM || OP == FFMA_DENORM) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) r[j] = (r[j] & 0x3FFFF) | 0x400;        // denormal bit patterns (< 2^23)
+#pragma unroll
+        for (int j = 0; j < 8; j++) q[j] = ((unsigned long long)r[2 * j] << 32) | r[2 * j + 1];
+    }
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -28,12 +34,16 @@ __global__ void __launch_bounds__(1024, 1) k(int iters, const int *in, int *out)
             if (OP == IMAD) asm volatile("mad.lo.s32 %0, %0, 3, 0x4B400000;" : "+r"(r[j]));
             if (OP == FADD) asm volatile("add.rn.f32 %0, %0, 0fCB400000;" : "+r"(r[j]));
             if (OP == FFMA) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+r"(r[j]));
+            if (OP == FFMA_DENORM) asm volatile("fma.rn.f32 %0, %0, 0f3F800000, 0f00000000;" : "+r"(r[j]));
             if (OP == LOP3) asm volatile("lop3.b32 %0, %0, 0xF0F0F0F0, %1, 0x6A;" : "+r"(r[j]) : "r"(i));
         }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             if (OP == FADD2) asm volatile("add.rn.f32x2 %0, %0, %0;" : "+l"(q[j]));
             if (OP == FFMA2) asm volatile("fma.rn.f32x2 %0, %0, %0, %0;" : "+l"(q[j]));
+            if (OP == FFMA2_DENORM) {   // operands stay denormal: x = x * 1.0 + 0 with x = small integer bit pattern
+                asm volatile("{.reg .b64 o, z; mov.b64 o, 0x3F8000003F800000; mov.b64 z, 0; fma.rn.f32x2 %0, %0, o, z;}" : "+l"(q[j]));
+            }
             if (OP == IMADWIDE) asm volatile("mad.wide.s32 %0, %1, %1, %0;" : "+l"(q[j]) : "r"(r[j]));
             if (OP == MIX_I2FP_FFMA2) {      // the current epilogue: 2 I2FP + 1 FFMA2 per 2 elements
                 asm volatile("cvt.rn.f32.s32 %0, %0;" : "+r"(r[2 * j]));
@@ -102,6 +112,8 @@ int main()
     int h[1024]; for (int i = 0; i < 1024; i++) h[i] = (i * 7919) % 4001 - 2000;
     CK(cudaMemcpy(in, h, 4096, cudaMemcpyHostToDevice));
     printf("device %s, %d SMs, max clock %d MHz (rates assume the max clock)\n", prop.name, sms, clk_khz / 1000);
+    run<FFMA_DENORM>("FFMA denormal operand", 16, 0, sms, clk_khz, in, out);
+    run<FFMA2_DENORM>("FFMA2 denormal operand", 8, 0, sms, clk_khz, in, out);
     run<I2FP>("I2FP.F32.S32", 16, 0, sms, clk_khz, in, out);
     run<IADD3>("IADD (add.s32 imm)", 16, 0, sms, clk_khz, in, out);
     run<IMAD>("IMAD (mad.lo imm)", 16, 0, sms, clk_khz, in, out);
