@@ -31,13 +31,14 @@
 // Data flow per CTA (persistent, one CTA per SM, contiguous range of work items;
 // item = (channel, 256-column tile), 4 M-tiles per item):
 //   warp 0      TMA producer: cp.async.bulk packed voltages -> staging ring (4 x 16 KB)
-//   warp 1      MMA issuer (one thread): 4 x tcgen05.mma M128 N256 K32 per M-tile,
+//   warp 1      MMA issuer (one thread): 1 bias + 4 data tcgen05.mma M128 N256 K32 per M-tile,
 //               TMEM accumulators double-buffered (2 x 256 columns)
 //   warp 2      weights loader (cp.async.bulk of the pre-swizzled A' tiles) + TMEM alloc
 //   warp 3      idle
-//   warps 4-11  epilogue: tcgen05.ld -> square/accumulate over G columns -> one
-//               shuffle to add re^2+im^2 rows -> coalesced float stores
-//   warps 12-15 unpack: staging -> sign-preserving nibble split -> SW128 K-major B' tile
+//   warps 4-7   unpack: staging -> nibble split (x+8, unsigned) -> SW128 K-major B' tile
+//   warps 8-23  epilogue, two groups of 8 warps, one per TMEM stage (so they run half a
+//               period apart): tcgen05.ld -> un-bias + square/accumulate over G columns
+//               -> one shuffle to add re^2+im^2 rows -> coalesced float stores
 // Voltages are read from HBM once, weights once per (CTA, channel); nothing but
 // the final float power is written.
 #include "fused_beamform.cuh"
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
         for (int i = 0; i < kStages; i++) { mbar_init(&sm.stg_full[i], 1); mbar_init(&sm.stg_empty[i], kNumUnpackWarps); }
         for (int i = 0; i < 2; i++) {
             mbar_init(&sm.b_full[i], kNumUnpackWarps); mbar_init(&sm.b_empty[i], 1);
-            mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps);
+            mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps);   // 8 warps x 2 chunks per stage
         }
         for (int i = 0; i < kMaxMT; i++) { mbar_init(&sm.a_full[i], 1); mbar_init(&sm.a_empty[i], 1); }
         fence_mbar_init();
@@ -374,13 +375,19 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
         }
     } else {
         // ================= epilogue: TMEM -> |V|^2 summed over G columns -> float power =================
+        // The 16 warps form two groups of 8; group g owns TMEM stage g, i.e. every second M-tile.  A
+        // warp covers its lane quarter x 128 columns of its stage in two 64-column chunks.  The two
+        // groups are therefore always half a period apart: while one waits for the tensor core or
+        // for its TMEM loads, the other is in its arithmetic phase on the same SM sub-partitions.
         setmaxnreg_inc<kRegsEpi>();
         const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-        const int wc = ew >> 2;                    // which 64 columns of the tile
+        const int grp_id = ew >> 3;                // 0/1: which TMEM stage this warp serves
+        const int half = (ew >> 2) & 1;            // which 128 columns of the tile
         const int row = quarter * 32 + lane;       // A' row: beam = row/2, component = row&1
-        uint32_t tbase_w = tmem_base + ((uint32_t)(quarter * 32) << 16) + wc * kEpiCols;
+        uint32_t tbase_w = tmem_base + ((uint32_t)(quarter * 32) << 16) + grp_id * kAccCols + half * 128;
         asm volatile("" : "+r"(tbase_w));
+        const uint32_t bar_full_w = bar_acc_full + 8 * grp_id, bar_empty_w = bar_acc_empty + 8 * grp_id;
         constexpr int kGroups = kEpiCols / G;
         EpiCtx<EXACT> ctx;
         ctx.lane_odd = lane & 1;
@@ -389,39 +396,39 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
         // fp32 mode carries V * 2^-23, so the power carries 2^-46
         ctx.scale = EXACT ? p.scale : p.scale * 70368744177664.0f;
         const int32_t *crow_w = p.crow + row;
-        uint32_t acc_cnt = 0;
+        // stage sequence number n = (local item index) * mt + m; this group takes n = grp_id, grp_id+2, ...
+        const int n_stages = (item_end - item_begin) * mt;
+        int item = item_begin, m = grp_id;
+        while (m >= mt) { m -= mt; item++; }
+        uint32_t use = 0;                           // how many times this group's stage has been used
 #pragma unroll 1
-        for (int item = item_begin; item < item_end; item++) {
+        for (int n = grp_id; n < n_stages; n += 2, use++) {
             const int f = item / g.n_tiles, t = item - f * g.n_tiles;
-            const int colbase = t * kTileN + wc * kEpiCols;          // first global column of this warp
-            const int cols_left = g.n_cols_total - colbase;
-            ctx.vg_lane = (cols_left >= kEpiCols ? kGroups : (cols_left > 0 ? cols_left / G : 0)) - ctx.lane_odd;
-            // even lanes (re rows) store the even group of each pair, odd lanes the odd group
-            const size_t out_off = ((size_t)(colbase / G) + ((kGroups > 1) ? ctx.lane_odd : 0)) * tstride + (size_t)f * p.n_beams + (row >> 1);
-            float *out_item = p.out + out_off;
-            asm volatile("" : "+l"(out_item));                       // keep the pointer live; do not recompute per M-tile
-            long long *pp_item = (EXACT && p.pdump) ? p.pdump + out_off : nullptr;
+            const int c_row = __ldg(crow_w + ((size_t)f * mt + m) * 128);       // issued before the wait: latency hidden
+            mbar_wait(bar_full_w, use & 1, 8);
+            tc_fence_after();
 #pragma unroll 1
-            for (int m = 0; m < mt; m++, acc_cnt++) {
-                const uint32_t as = acc_cnt & 1;
-                const int c_row = __ldg(crow_w + ((size_t)f * mt + m) * 128);       // issued before the wait: latency hidden
-                mbar_wait(bar_acc_full + 8 * as, (acc_cnt >> 1) & 1, 8);
-                tc_fence_after();
-                const uint32_t taddr = tbase_w + as * kAccCols;
+            for (int chunk = 0; chunk < 2; chunk++) {
+                const int colbase = t * kTileN + half * 128 + chunk * kEpiCols;  // first global column of this chunk
                 uint32_t va[32], vb[32];
-                tmem_ld_32x32(taddr, va);
-                tmem_ld_32x32(taddr + 32, vb);
+                tmem_ld_32x32(tbase_w + chunk * kEpiCols, va);
+                tmem_ld_32x32(tbase_w + chunk * kEpiCols + 32, vb);
                 tmem_ld_wait(va);
                 tmem_ld_wait(vb);
-                // both halves are in registers: hand the TMEM stage back to the MMA right away
+                // this chunk is in registers: count it towards handing the stage back to the MMA (the
+                // stage is free once all 8 warps x 2 chunks have arrived)
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+                if (lane == 0) mbar_arrive(bar_empty_w);
                 // ptxas sinks the arrive below all of the math that follows (it has no consumers), which
                 // keeps the TMEM stage -- and so the tensor pipe -- waiting.  A never-taken, runtime-opaque
                 // branch ends the basic block here and pins it.
-                if (acc_cnt == 0xFFFFFFFFu) continue;
+                if (use == 0xFFFFFFFFu) continue;
 
+                const int cols_left = g.n_cols_total - colbase;
+                ctx.vg_lane = (cols_left >= kEpiCols ? kGroups : (cols_left > 0 ? cols_left / G : 0)) - ctx.lane_odd;
+                // even lanes (re rows) store the even group of each pair, odd lanes the odd group
+                const size_t out_off = ((size_t)(colbase / G) + ((kGroups > 1) ? ctx.lane_odd : 0)) * tstride + (size_t)f * p.n_beams + m * 64 + (row >> 1);
                 if (DUMP) {
                     // debug tap: int32 voltages, [f][col][beam][2]; this thread's (beam, component) = row
                     int32_t *vd = p.vdump + ((size_t)f * g.n_cols_total * p.n_beams + m * 64) * 2 + row;
@@ -435,13 +442,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 ctx.acc.set_row_const(c_row);
                 ctx.acc.zero();
                 ctx.pend = 0;
-                ctx.op = out_item;
-                ctx.pp = pp_item;
+                ctx.op = p.out + out_off;
+                ctx.pp = (EXACT && p.pdump) ? p.pdump + out_off : nullptr;
                 epi_block<G, EXACT, 0>(ctx, va);
                 epi_block<G, EXACT, 1>(ctx, vb);
-                out_item += 64;                                      // next M-tile = next 64 beams
-                if (EXACT) { if (pp_item) pp_item += 64; }
             }
+            m += 2;
+            while (m >= mt) { m -= mt; item++; }
         }
     }
 
