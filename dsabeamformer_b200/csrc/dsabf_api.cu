@@ -51,7 +51,7 @@ struct dsabf_handle {
     int group = 0;            // columns per output = n_pol * n_averaging
     int cols_per_chunk = 0;
     size_t chunk_bytes = 0, block_bytes = 0, chunk_out_floats = 0;
-    float scale = 0.f;        // power_scale
+    float scale = 0.f;        // power_scale / 256
     bool weights_set = false;
 
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
@@ -60,7 +60,6 @@ struct dsabf_handle {
     float *d_ded = nullptr;        // n_ring_slots * n_chunks_per_block * n_beams
     int8_t *d_w = nullptr;         // reference-layout weights
     uint8_t *d_wprep = nullptr;    // tensor-core layout
-    int32_t *d_crow = nullptr;     // per-row accumulator constants
     int *d_bad = nullptr;
 
     std::vector<cudaEvent_t> ev_slot_h2d, ev_slot_comp, ev_slot_d2h;   // per ring slot
@@ -106,7 +105,6 @@ int run_fused(dsabf_handle *h, const uint8_t *d_packed, int n_chunks, float *d_o
     dsabf::FusedParams p{};
     p.packed = d_packed;
     p.wprep = h->d_wprep;
-    p.crow = h->d_crow;
     p.out = d_out;
     p.vdump = vdump;
     p.pdump = pdump;
@@ -205,7 +203,7 @@ int dsabf_create(const dsabf_config *cfg, dsabf_handle **out)
     // reference: alpha = (float)(1.0/127) applied to both components (beamformer.cu:191), squared by detect_sum
     const float alpha = (float)(1.0 / 127);
     const float ps = cfg->power_scale != 0.f ? cfg->power_scale : (float)((double)alpha * (double)alpha);
-    h->scale = ps;
+    h->scale = ps / 256.0f;
 
     int rc = 0;
     auto ck = [&](cudaError_t e, const char *w) { if (e != cudaSuccess && !rc) rc = fail((int)e, w); };
@@ -219,7 +217,6 @@ int dsabf_create(const dsabf_config *cfg, dsabf_handle **out)
     const size_t wbytes = (size_t)cfg->n_channels * cfg->n_antennas * cfg->n_beams * 2;
     ck(cudaMalloc(&h->d_w, wbytes), "alloc weights");
     ck(cudaMalloc(&h->d_wprep, 2 * wbytes), "alloc tensor-core weights");   // realified: 2 rows of 2*n_ant bytes per beam
-    ck(cudaMalloc(&h->d_crow, (size_t)cfg->n_channels * cfg->n_beams * 2 * sizeof(int32_t)), "alloc row constants");
     ck(cudaMalloc(&h->d_bad, sizeof(int)), "alloc flag");
     if (!rc) {
         ck(cudaMemset(h->d_ring, 0, slots * h->block_bytes), "memset ring");           // beamformer.cu:291-298
@@ -256,7 +253,7 @@ int dsabf_destroy(dsabf_handle *h)
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
-    cudaFree(h->d_ring); cudaFree(h->d_out); cudaFree(h->d_ded); cudaFree(h->d_w); cudaFree(h->d_wprep); cudaFree(h->d_crow); cudaFree(h->d_bad);
+    cudaFree(h->d_ring); cudaFree(h->d_out); cudaFree(h->d_ded); cudaFree(h->d_w); cudaFree(h->d_wprep); cudaFree(h->d_bad);
     cudaFree(h->d_tmp_in); cudaFree(h->d_tmp_out);
     delete h;
     return 0;
@@ -304,7 +301,7 @@ int dsabf_set_weights(dsabf_handle *h, const int8_t *w)
     CK(cudaStreamSynchronize(h->s_comp));
     CK(cudaMemcpyAsync(h->d_w, w, wbytes, cudaMemcpyHostToDevice, h->s_comp));
     CK(cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->s_comp));
-    CK(dsabf::launch_prep_weights(h->d_w, h->d_wprep, h->d_crow, c.n_channels, c.n_antennas, c.n_beams, h->d_bad, h->s_comp));
+    CK(dsabf::launch_prep_weights(h->d_w, h->d_wprep, c.n_channels, c.n_antennas, c.n_beams, h->d_bad, h->s_comp));
     h->launches++;
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->s_comp));
