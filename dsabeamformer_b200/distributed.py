@@ -1,0 +1,70 @@
+"""Multi-GPU plumbing: channel sharding and the one exchange the path has.
+
+Unpack + beamform + detect shard by frequency with no communication: the reference already runs
+8 independent `beam -g <0..7>` processes of 256 of the 2048 channels (/root/reference/src/
+beamformer.hh:63-64; README.md:168).  Only full-band dedispersion needs data from every channel,
+so the detected power is transposed from "all beams of my channels" to "all channels of my beams"
+with ONE all-to-all (NCCL over NVLink on GPUs; gloo in the CPU tests), then dedispersed locally.
+torch.distributed is the plumbing; the kernels are the library's.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+TOT_CHANNELS, N_SUBBANDS = 2048, 8
+
+
+def subband_of_rank(rank):
+    """`-g` of the reference: rank r beamforms sub-band r (integer offset r*2048/7 channels, beamformer.cu:233)."""
+    return rank % N_SUBBANDS
+
+
+def channel_range(rank, world, n_channels_total):
+    """Contiguous channel shard of `rank` (equal shards; n_channels_total % world == 0)."""
+    assert n_channels_total % world == 0
+    per = n_channels_total // world
+    return rank * per, (rank + 1) * per
+
+
+def beam_range(rank, world, n_beams):
+    assert n_beams % world == 0
+    per = n_beams // world
+    return rank * per, (rank + 1) * per
+
+
+def subband_frequencies_ghz(gpu, n_chan=256):
+    """Channel centre frequencies of sub-band `gpu` as the steering weights see them (beamformer.cu:233)."""
+    bw = np.float32((1.53 - 1.28) / TOT_CHANNELS)
+    idx = gpu * TOT_CHANNELS // (N_SUBBANDS - 1) + np.arange(n_chan)
+    return (1.53 - (idx.astype(np.float32) * bw).astype(np.float64)).astype(np.float32).astype(np.float64)
+
+
+def freq_to_beam_all_to_all(power_local, group=None):
+    """power_local: [T][ch_local][B] (all beams, my channels) on every rank  ->  [T][ch_local*world][B/world]
+    (all channels in rank order, my beams).  One all_to_all_single; message to each peer is
+    T*ch_local*(B/world) floats."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    T, C, B = power_local.shape
+    assert B % world == 0
+    Bs = B // world
+    if world == 1:
+        return power_local
+    # [T][C][world][Bs] -> [world][T][C][Bs]: chunk h goes to rank h
+    send = power_local.reshape(T, C, world, Bs).permute(2, 0, 1, 3).contiguous()
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    # recv[g] = rank g's channels for my beams -> [T][g*C + c][Bs]
+    return recv.permute(1, 0, 2, 3).reshape(T, world * C, Bs).contiguous()
+
+
+def dedisperse_full_band(beamformer, power_local, delay_full, n_t_out, group=None):
+    """Full-band incoherent dedispersion across ranks.  delay_full: int32 [n_dm][ch_local*world] in the
+    global channel order (rank-major).  Returns this rank's beams: [n_dm][n_t_out][B/world] (CUDA tensor)."""
+    full = freq_to_beam_all_to_all(power_local, group)
+    T, C, Bs = full.shape
+    n_dm = delay_full.shape[0]
+    out = torch.empty((n_dm, n_t_out, Bs), dtype=torch.float32, device=full.device)
+    beamformer.dedisperse_device(full.data_ptr(), T, C, Bs, np.ascontiguousarray(delay_full, dtype=np.int32), n_t_out, out.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream)
+    return out
