@@ -51,7 +51,7 @@ struct dsabf_handle {
     int group = 0;            // columns per output = n_pol * n_averaging
     int cols_per_chunk = 0;
     size_t chunk_bytes = 0, block_bytes = 0, chunk_out_floats = 0;
-    float scale = 0.f;        // power_scale / 256
+    float scale = 0.f;        // power_scale
     bool weights_set = false;
 
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
@@ -61,6 +61,7 @@ struct dsabf_handle {
     int8_t *d_w = nullptr;         // reference-layout weights
     uint8_t *d_wprep = nullptr;    // tensor-core layout
     int *d_bad = nullptr;
+    long long *d_trace = nullptr;  // debug: clock64 trace buffer (dsabf_debug_trace)
 
     std::vector<cudaEvent_t> ev_slot_h2d, ev_slot_comp, ev_slot_d2h;   // per ring slot
     std::vector<char> slot_has_h2d, slot_has_comp, slot_has_d2h;
@@ -108,6 +109,7 @@ int run_fused(dsabf_handle *h, const uint8_t *d_packed, int n_chunks, float *d_o
     p.out = d_out;
     p.vdump = vdump;
     p.pdump = pdump;
+    p.trace = h->d_trace;
     p.n_chan = h->cfg.n_channels;
     p.n_chunks = n_chunks;
     p.cols_per_chunk = h->cols_per_chunk;
@@ -203,7 +205,7 @@ int dsabf_create(const dsabf_config *cfg, dsabf_handle **out)
     // reference: alpha = (float)(1.0/127) applied to both components (beamformer.cu:191), squared by detect_sum
     const float alpha = (float)(1.0 / 127);
     const float ps = cfg->power_scale != 0.f ? cfg->power_scale : (float)((double)alpha * (double)alpha);
-    h->scale = ps / 256.0f;
+    h->scale = ps;
 
     int rc = 0;
     auto ck = [&](cudaError_t e, const char *w) { if (e != cudaSuccess && !rc) rc = fail((int)e, w); };
@@ -445,6 +447,23 @@ int dsabf_debug_voltages_host(dsabf_handle *h, const void *packed, int n_chunks,
     if (d_p) cudaFree(d_p);
     if (rc) return rc;
     if (e != cudaSuccess) return fail((int)e, "debug voltages");
+    return 0;
+}
+
+// debug: run one fused launch on device-resident data with the in-kernel clock trace on; trace_out: 2048 int64
+int dsabf_debug_trace(dsabf_handle *h, const void *d_packed, int n_chunks, float *d_out, long long *trace_out)
+{
+    if (!h || !d_packed || !d_out || !trace_out) return fail(DSABF_E_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMalloc(&h->d_trace, 2048 * sizeof(long long)));
+    CK(cudaMemset(h->d_trace, 0, 2048 * sizeof(long long)));
+    int rc = run_fused(h, (const uint8_t *)d_packed, n_chunks, d_out, nullptr, nullptr, h->cfg.exact_power != 0, h->s_comp);
+    cudaError_t e = cudaStreamSynchronize(h->s_comp);
+    if (!rc && e == cudaSuccess) e = cudaMemcpy(trace_out, h->d_trace, 2048 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(h->d_trace);
+    h->d_trace = nullptr;
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail((int)e, "trace");
     return 0;
 }
 

@@ -12,13 +12,14 @@ struct FusedParams {
     float *out;              // [n_chunks*cols_per_chunk/group][n_chan][n_beams] power
     int32_t *vdump;          // optional: [n_chan][n_chunks*cols_per_chunk][n_beams][2] int32 voltages
     long long *pdump;        // optional (exact mode): integer power, same shape as out
+    long long *trace;        // optional: clock64 trace of CTA 0 (debug), 128 stages x 16 slots
     int n_chan;
     int n_chunks;
     int cols_per_chunk;      // N_TIMESTEPS_PER_GEMM
     int group;               // columns summed per output = n_pol * n_averaging
     int n_beams;             // multiple of 64, <= 256
     int n_tiles;             // ceil(n_chunks*cols_per_chunk / 256)
-    float scale;             // power_scale / 256 (voltages are carried x16)
+    float scale;             // power_scale: multiplies the integer power
 };
 
 cudaError_t launch_fused_beamform(const FusedParams &p, bool exact, int num_sms, cudaStream_t stream);
