@@ -205,7 +205,7 @@ int dsabf_create(const dsabf_config *cfg, dsabf_handle **out)
     // reference: alpha = (float)(1.0/127) applied to both components (beamformer.cu:191), squared by detect_sum
     const float alpha = (float)(1.0 / 127);
     const float ps = cfg->power_scale != 0.f ? cfg->power_scale : (float)((double)alpha * (double)alpha);
-    h->scale = ps;
+    h->scale = ps / 256.0f;      // voltages are carried x16 through the tensor core
 
     int rc = 0;
     auto ck = [&](cudaError_t e, const char *w) { if (e != cudaSuccess && !rc) rc = fail((int)e, w); };

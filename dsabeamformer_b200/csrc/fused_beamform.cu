@@ -13,27 +13,16 @@
 //     [Vre; Vim] = [[Wre, -Wim], [Wim, Wre]] [Xre; Xim]
 // A' (weights) rows are interleaved (row 2i = re of beam i, row 2i+1 = im), K' =
 // 2*64 antennas = 128 bytes = exactly one SWIZZLE_128B row, so one M=128 tile is
-// 64 beams and a 256-beam channel is 4 resident 16 KB tiles.
-//
-// The epilogue, not the tensor core, bounds this kernel: every int32 accumulator
-// receives only K' = 128 MACs, so at tensor peak 64 accumulators per clock per SM
-// have to be converted and squared.  Measured B200 pipe rates (profiles/
-// r01_ubench_pipe_rates.txt): I2FP issues at half rate on the ALU pipe, FFMA/FFMA2
-// at full rate on the FMA pipe, also with denormal operands.  So the work is split
-// over both pipes (G <= 32):
-//  * columns 128..255 of a tile: I2FP (ALU) + packed fma.rn.f32x2 square-accumulate;
-//  * columns 0..127: one extra MMA (K = 32 bytes of constants: 64 x 64 for these columns, 64 x 0
-//    for the others) pre-loads these accumulators with 2^17 > max|V|, so I = 2^17 + V is in (0, 2^23) and its bit
-//    pattern read as fp32 is the DENORMAL I*2^-149 -- already a float, linear in V.
-//    One FFMA2, f = I*2^-149 * 2^126 - 2^-6 = V*2^-23 (exact), replaces the two I2FP;
-//    the factor 2^46 of |f|^2 is folded into the output scale of those columns.
-// Each epilogue warp takes 32 columns of either kind, so both pipes stay busy.
+// 64 beams and a 256-beam channel is 4 resident 16 KB tiles.  X is NOT shifted
+// down when unpacked: the nibbles are left in the high half of each byte
+// (x' = 16 x), so unpacking is 2 LOP3 + 1 SHF per 4 samples; V' = 16 V stays
+// < 2^22, and the factor 256 in the power is folded into the output scale.
 //
 // Data flow per CTA (persistent, one CTA per SM, contiguous range of work items;
 // item = (channel, 256-column tile), 4 M-tiles per item):
 //   warp 0      TMA producer: cp.async.bulk packed voltages -> staging ring (4 x 16 KB)
-//   warps 1, 3  MMA issuers (one thread each, one per TMEM accumulator stage): 1 constant + 4 data
-//               tcgen05.mma M128 N256 K32 per M-tile, accumulators double-buffered (2 x 256 TMEM columns)
+//   warps 1, 3  MMA issuers (one thread each, one per TMEM accumulator stage): 4 x tcgen05.mma
+//               M128 N256 K32 per M-tile, accumulators double-buffered (2 x 256 TMEM columns)
 //   warp 2      weights loader (cp.async.bulk of the pre-swizzled A' tiles) + TMEM alloc
 //   warps 4-11  epilogue: tcgen05.ld -> square/accumulate over G columns -> one
 //               shuffle to add re^2+im^2 rows -> coalesced float stores
@@ -58,9 +47,6 @@ constexpr int kBTileBytes = kTileN * kRowBytes; // 32 KB: unpacked voltages tile
 constexpr int kStageBytes = kTileN * 64;        // 16 KB: packed voltages tile
 constexpr int kStages = 4;
 constexpr int kMaxMT = 4;
-constexpr int kBiasABytes = 128 * 32;    // 4 KB of 0x40: A operand of the bias MMA (M=128, K=32)
-constexpr int kBiasBBytes = kTileN * 32; // 8 KB: B operand (N=256, K=32): rows 0..127 = 0x40, rows 128..255 = 0
-constexpr int kBias = 1 << 17;           // 32 * 64 * 64: what the bias MMA puts into columns 0..127
 constexpr int kAccCols = 256;            // TMEM columns per accumulator stage
 constexpr int kTmemCols = 512;
 
@@ -69,14 +55,13 @@ constexpr int kTmemCols = 512;
 constexpr int kUnpackWarp0 = 4, kNumUnpackWarps = 4;
 constexpr int kEpiWarp0 = 8, kNumEpiWarps = 16;
 constexpr int kThreads = (kEpiWarp0 + kNumEpiWarps) * 32;   // 768
+constexpr int kEpiCols = kTileN / (kNumEpiWarps / 4);       // 64 columns per epilogue warp
 constexpr int kRegsLight = 40, kRegsEpi = 96;               // setmaxnreg budgets (launch: 80)
 
 struct __align__(1024) Smem {
     uint8_t a[kMaxMT][kATileBytes];      // 64 KB  resident weights of the current channel
     uint8_t b[2][kBTileBytes];           // 64 KB  unpacked voltages, double buffered
     uint8_t stg[kStages][kStageBytes];   // 64 KB  packed voltages ring
-    uint8_t bias_a[kBiasABytes];         //  4 KB  constant 64 (s8)
-    uint8_t bias_b[kBiasBBytes];         //  8 KB  64 for columns 0..127, 0 for columns 128..255
     uint64_t stg_full[kStages], stg_empty[kStages];
     uint64_t b_full[2], b_empty[2];
     uint64_t a_full[kMaxMT], a_empty[kMaxMT];
@@ -84,21 +69,21 @@ struct __align__(1024) Smem {
     uint32_t tmem_base;
 };
 
-// Square-accumulate of one row's voltages in the two supported arithmetic modes.  BIASED
-// columns hold I = 2^17 + V, the others V.  Several independent partial sums keep the
-// dependent chains short.
+// Square-accumulate of one row's voltages in the two supported arithmetic modes.
+// Both keep several independent partial sums so that consecutive columns do not
+// form one long dependent chain.
 //  EXACT : int64 via mad.wide.s32 (IMAD.WIDE) -- integer power exact, slower.
-//  fast  : fp32, two columns per packed fma.rn.f32x2 (FFMA2).  Exact whenever the integer power
-//          is < 2^24 (every partial sum is then exactly representable); otherwise <= G * 2^-24
-//          relative (~1e-7 typical).  Biased groups carry V*2^-23, i.e. power * 2^-46.
+//  fast  : fp32; two columns at a time are converted (I2FP) and fed to one packed
+//          fma.rn.f32x2 (FFMA2).  Exact whenever the integer power is < 2^24
+//          (every partial sum is then an exactly representable integer multiple
+//          of 256); otherwise <= G * 2^-24 relative, ~1e-7 typical.
 template <bool EXACT> struct Acc;
 template <> struct Acc<true> {
     using sum_t = long long;
     long long s0, s1, s2, s3;
     __device__ __forceinline__ void zero() { s0 = s1 = s2 = s3 = 0; }
-    template <int SLOT, bool BIASED> __device__ __forceinline__ void add2(int i0, int i1)
+    template <int SLOT> __device__ __forceinline__ void add2(int v0, int v1)
     {
-        const int v0 = BIASED ? i0 - kBias : i0, v1 = BIASED ? i1 - kBias : i1;
         if (SLOT == 0) {
             asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s0) : "r"(v0));
             asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s1) : "r"(v1));
@@ -107,29 +92,20 @@ template <> struct Acc<true> {
             asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s3) : "r"(v1));
         }
     }
+    // sum of the first NSLOT packed slots that were used since zero()
     template <int NSLOT> __device__ __forceinline__ long long sum() const { return NSLOT == 1 ? (s0 + s1) : (s0 + s1) + (s2 + s3); }
 };
 template <> struct Acc<false> {
     using sum_t = float;
     unsigned long long a0, a1;     // two packed float2 accumulators
     __device__ __forceinline__ void zero() { a0 = 0ull; a1 = 0ull; }
-    template <int SLOT, bool BIASED> __device__ __forceinline__ void add2(int i0, int i1)
+    template <int SLOT> __device__ __forceinline__ void add2(int v0, int v1)
     {
-        if (BIASED) {
-            // t = (I * 2^-149) * 2^126 - 2^17 * 2^-23 = V * 2^-23; 0x7E800000 = 2^126, 0xBC800000 = -2^-6
-            if (SLOT == 0)
-                asm("{.reg .b64 t, s, c; mov.b64 t, {%1, %2}; mov.b64 s, 0x7E8000007E800000; mov.b64 c, 0xBC800000BC800000;"
-                    " fma.rn.f32x2 t, t, s, c; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a0) : "r"(i0), "r"(i1));
-            else
-                asm("{.reg .b64 t, s, c; mov.b64 t, {%1, %2}; mov.b64 s, 0x7E8000007E800000; mov.b64 c, 0xBC800000BC800000;"
-                    " fma.rn.f32x2 t, t, s, c; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a1) : "r"(i0), "r"(i1));
-        } else {
-            float f0, f1;
-            asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f0) : "r"(i0));
-            asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f1) : "r"(i1));
-            if (SLOT == 0) asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a0) : "f"(f0), "f"(f1));
-            else           asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a1) : "f"(f0), "f"(f1));
-        }
+        float f0, f1;
+        asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f0) : "r"(v0));
+        asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f1) : "r"(v1));
+        if (SLOT == 0) asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a0) : "f"(f0), "f"(f1));
+        else           asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a1) : "f"(f0), "f"(f1));
     }
     template <int NSLOT> __device__ __forceinline__ float sum() const
     {
@@ -140,12 +116,6 @@ template <> struct Acc<false> {
         return (a + b) + (c + d);
     }
 };
-
-// four packed 4-bit two's complement values (low nibble of every byte of w) -> four int8
-__device__ __forceinline__ uint32_t sext4(uint32_t w)
-{
-    return ((((w & 0x0F0F0F0Fu) ^ 0x88888888u) - 0x08080808u) ^ 0x80808080u);
-}
 
 // Work-item geometry shared by all roles.
 struct Geom {
@@ -159,70 +129,63 @@ struct Geom {
 template <bool EXACT> struct EpiCtx {
     using sum_t = typename Acc<EXACT>::sum_t;
     Acc<EXACT> acc;       // running sum of squares of the current group of G columns
-    sum_t pend;           // finished group waiting for its partner group
+    sum_t pend;           // finished even group waiting for the odd group of its pair
     int lane_odd;         // odd lanes hold im rows
-    int vg[2];            // valid groups in this warp's first / second 32-column block, minus lane_odd
-    float *op[2];         // &out[first group of the block + lane_odd][f][beam of this row]
-    long long *pp[2];     // same for the exact-power dump (nullptr = off)
-    size_t tstride;       // elements between consecutive output times
-    float scale[2];       // output scale of the two blocks (the biased block carries 2^-46)
+    int vg_lane;          // (valid groups of this warp's 64 columns) - lane_odd   (ragged last tile)
+    float *op;            // running pointer: &out[next group pair + lane_odd][f][beam of this row]
+    long long *pp;        // same for the exact-power dump (nullptr = off)
+    size_t pair_stride;   // elements between consecutive group pairs = 2 output times
+    float scale;
 };
 
+// Store the finished output of group pair PAIR (compile-time) and advance the pointers.
 template <bool EXACT>
-__device__ __forceinline__ void epi_store(const EpiCtx<EXACT> &c, typename EpiCtx<EXACT>::sum_t tot, int blk, int first_grp_of_pair)
+__device__ __forceinline__ void epi_store(EpiCtx<EXACT> &c, typename EpiCtx<EXACT>::sum_t tot, int first_grp_of_pair)
 {
-    if (first_grp_of_pair < c.vg[blk]) {
-        const size_t o = (size_t)first_grp_of_pair * c.tstride;
-        c.op[blk][o] = (float)tot * c.scale[blk];
+    if (first_grp_of_pair < c.vg_lane) {
+        *c.op = (float)tot * c.scale;
         if (EXACT) {
-            if (c.pp[blk]) c.pp[blk][o] = (long long)tot;
+            if (c.pp) *c.pp = (long long)tot >> 8;
         }
+    }
+    c.op += c.pair_stride;
+    if (EXACT) {
+        if (c.pp) c.pp += c.pair_stride;
     }
 }
 
-// One 32-column block (BLK 0/1 of this warp's two): square, sum per group of G columns, combine the
-// re row (even lane) with the im row (odd lane) by one shuffle per two groups: even lanes finish the
-// first group of a pair, odd lanes the second, so a warp stores 2 x 64 contiguous bytes per pair.
-//  G < 32 : pairs are consecutive groups inside the block.
-//  G = 32 : the pair is (block 0, block 1): block 0 parks its sum, block 1 exchanges and stores.
-//  G = 64 : one group over both blocks; only even lanes store.
-template <int G, bool EXACT, int BLK, bool BIASED>
+// 32 accumulator columns [BLK*32, BLK*32+32) of this warp's 64: square, sum per
+// group of G columns, and on every second finished group exchange with the lane
+// holding the other component (re rows = even lanes, im rows = odd lanes): even
+// lanes finish the even group of the pair, odd lanes the odd group, so one
+// shuffle yields two outputs and a warp stores 2 x 64 contiguous bytes.
+template <int G, bool EXACT, int BLK>
 __device__ __forceinline__ void epi_block(EpiCtx<EXACT> &c, const uint32_t (&v)[32])
 {
+    constexpr int kGroups = kEpiCols / G;                 // groups per warp: 32,16,8,4,2,1
     constexpr int kSlots = (G >= 4) ? 2 : 1;              // packed accumulator slots in use
 #pragma unroll
     for (int jj = 0; jj < 32; jj += 2) {
-        if (kSlots == 1 || ((jj >> 1) & 1) == 0) c.acc.template add2<0, BIASED>((int)v[jj], (int)v[jj + 1]);
-        else                                     c.acc.template add2<1, BIASED>((int)v[jj], (int)v[jj + 1]);
-        const int cl = jj + 1;                     // last column of the block handled so far (compile-time)
-        if (G <= 32 && ((cl + 1) % G) == 0) {
-            const int grp = cl / G;                // group index inside the block
+        if (kSlots == 1 || ((jj >> 1) & 1) == 0) c.acc.template add2<0>((int)v[jj], (int)v[jj + 1]);
+        else                                     c.acc.template add2<1>((int)v[jj], (int)v[jj + 1]);
+        const int cl = BLK * 32 + jj + 1;          // last column handled so far (compile-time after unrolling)
+        if (((cl + 1) % G) == 0) {
+            const int grp = cl / G;
             const auto sgrp = c.acc.template sum<kSlots>();
             c.acc.zero();
-            if (G == 32) {
-                if (BLK == 0) {
-                    c.pend = sgrp;
-                } else {
-                    const auto send = c.lane_odd ? c.pend : sgrp;        // even lanes finish block 0's group, odd lanes block 1's
-                    const auto mine = c.lane_odd ? sgrp : c.pend;
-                    const auto tot = mine + __shfl_xor_sync(0xffffffffu, send, 1);
-                    if (c.lane_odd) epi_store<EXACT>(c, tot, 1, 0);
-                    else            epi_store<EXACT>(c, tot, 0, 0);
-                }
+            if (kGroups == 1) {
+                const auto tot = sgrp + __shfl_xor_sync(0xffffffffu, sgrp, 1);
+                // single group: only the even lanes (vg_lane = valid - 0) store
+                if (!c.lane_odd) epi_store<EXACT>(c, tot, 0);
             } else if ((grp & 1) == 0) {
                 c.pend = sgrp;
             } else {
                 const auto send = c.lane_odd ? c.pend : sgrp;
                 const auto mine = c.lane_odd ? sgrp : c.pend;
                 const auto tot = mine + __shfl_xor_sync(0xffffffffu, send, 1);
-                epi_store<EXACT>(c, tot, BLK, grp - 1);
+                epi_store<EXACT>(c, tot, grp - 1);
             }
         }
-    }
-    if (G == 64 && BLK == 1) {
-        const auto sgrp = c.acc.template sum<kSlots>();
-        const auto tot = sgrp + __shfl_xor_sync(0xffffffffu, sgrp, 1);
-        if (!c.lane_odd) epi_store<EXACT>(c, tot, 0, 0);
     }
 }
 
@@ -233,7 +196,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
 {
     constexpr bool EXACT = MODE != 0;
     constexpr bool DUMP = MODE == 2;
-    constexpr bool kMixed = G <= 32;      // columns 0..127 of every tile carry the 2^17 bias (see header)
     extern __shared__ uint8_t smem_raw[];
     // align in the shared address space (keeps every later address a cheap 32-bit add)
     uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -259,13 +221,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
         fence_mbar_init();
     }
     if (warp == 2) { tmem_alloc(&sm.tmem_base, kTmemCols); tmem_relinquish(); }
-    // constant operand of the bias MMA (read by the tensor core through the async proxy)
-    for (int i = threadIdx.x; i < kBiasABytes / 16; i += kThreads) reinterpret_cast<uint4 *>(sm.bias_a)[i] = make_uint4(0x40404040u, 0x40404040u, 0x40404040u, 0x40404040u);
-    for (int i = threadIdx.x; i < kBiasBBytes / 16; i += kThreads) {
-        const uint32_t v = (i < kBiasBBytes / 32) ? 0x40404040u : 0u;      // 8-row groups are 256 B apart: first half = columns 0..127
-        reinterpret_cast<uint4 *>(sm.bias_b)[i] = make_uint4(v, v, v, v);
-    }
-    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -329,8 +284,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
             // trace, profiles/r01_mma_issue_trace.txt); with two threads one's waits overlap the other's MMAs.
             const int me = (warp == 3) ? 1 : 0;
             constexpr uint32_t idesc = make_idesc_i8(128, kTileN);
-            const uint64_t bias_adesc = make_desc_k_nosw(sbase + (uint32_t)offsetof(Smem, bias_a));
-            const uint64_t bias_bdesc = make_desc_k_nosw(sbase + (uint32_t)offsetof(Smem, bias_b));
             int cur_f = -1, ch = -1;
             uint32_t acc_cnt = 0, use = 0;          // use: how often this issuer's stage has been filled
             for (int item = item_begin, it = 0; item < item_end; item++, it++) {
@@ -355,11 +308,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                     if (p.trace && blockIdx.x == 0 && acc_cnt < 128) { p.trace[acc_cnt * 16 + 0] = tr0; p.trace[acc_cnt * 16 + 1] = clock64(); }
                     const uint64_t adesc = make_desc_k_sw128(a_smem + m * kATileBytes);
                     const uint32_t d = tmem_base + me * kAccCols;
-                    // mixed: one constant MMA first (columns 0..127 := 2^17, columns 128..255 := 0), then the data
-                    if (kMixed) mma_i8_ss(d, bias_adesc, bias_bdesc, idesc, 0);
 #pragma unroll
                     for (int k = 0; k < kRowBytes / 32; k++)   // K = 32 bytes per instruction; +32 B = +2 in the descriptor
-                        mma_i8_ss(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kMixed || k > 0) ? 1 : 0);
+                        mma_i8_ss(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0);
                     tc_commit(bar_acc_full + 8 * me);
                     if (p.trace && blockIdx.x == 0 && acc_cnt < 128) p.trace[acc_cnt * 16 + 2] = clock64();
                     if (last_of_ch) tc_commit(bar_a_empty + 8 * m);
@@ -369,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
             }
         }
     } else if (warp < kEpiWarp0) {
-        // ================= unpack: 4-bit+4-bit -> sign-extended int8, into SW128 K-major B' =================
+        // ================= unpack: 4-bit+4-bit -> int8 (x16), into SW128 K-major B' =================
         setmaxnreg_dec<kRegsLight>();
         const int uw = warp - kUnpackWarp0;
         // lane -> (row r in an 8-column group, 16-byte antenna chunk c): chosen so that both the
@@ -393,11 +344,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
             for (int i = 0; i < (kTileN / 8) / kNumUnpackWarps; i++) {
                 const int grp = uw + i * kNumUnpackWarps;      // 8-column group
                 const uint4 v = lds128(src + grp * 512);
-                uint4 re, im;      // per byte: nibble n -> two's complement int8 ((n ^ 0x88) - 8) ^ 0x80, no carry between bytes
-                re.x = sext4(v.x >> 4); im.x = sext4(v.x);
-                re.y = sext4(v.y >> 4); im.y = sext4(v.y);
-                re.z = sext4(v.z >> 4); im.z = sext4(v.z);
-                re.w = sext4(v.w >> 4); im.w = sext4(v.w);
+                uint4 re, im;
+                re.x = v.x & 0xF0F0F0F0u; im.x = (v.x << 4) & 0xF0F0F0F0u;
+                re.y = v.y & 0xF0F0F0F0u; im.y = (v.y << 4) & 0xF0F0F0F0u;
+                re.z = v.z & 0xF0F0F0F0u; im.z = (v.z << 4) & 0xF0F0F0F0u;
+                re.w = v.w & 0xF0F0F0F0u; im.w = (v.w << 4) & 0xF0F0F0F0u;
                 sts128(dst + grp * 1024 + st_re, re);
                 sts128(dst + grp * 1024 + st_im, im);
             }
@@ -411,39 +362,29 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
         setmaxnreg_inc<kRegsEpi>();
         const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-        const int wc = ew >> 2;                    // 0..3: which columns of the tile
+        const int wc = ew >> 2;                    // which 64 columns of the tile
         const int row = quarter * 32 + lane;       // A' row: beam = row/2, component = row&1
-        // this warp's two 32-column blocks: mixed -> [wc*32, +32) (biased half) and [128 + wc*32, +32);
-        // otherwise 64 contiguous columns [wc*64, +64)
-        const int col_b0 = kMixed ? wc * 32 : wc * 64;
-        const int col_b1 = kMixed ? 128 + wc * 32 : wc * 64 + 32;
-        uint32_t tbase_w = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        uint32_t tbase_w = tmem_base + ((uint32_t)(quarter * 32) << 16) + wc * kEpiCols;
         asm volatile("" : "+r"(tbase_w));
-        constexpr int kGpb = (G <= 32) ? 32 / G : 1;               // groups per 32-column block
-        constexpr bool kLaneOff = G < 32;                          // odd lanes store the next output time (pairs inside a block)
+        constexpr int kGroups = kEpiCols / G;
         EpiCtx<EXACT> ctx;
         ctx.lane_odd = lane & 1;
-        ctx.tstride = (size_t)g.n_chan * p.n_beams;                // floats between consecutive output times
-        ctx.scale[0] = (kMixed && !EXACT) ? p.scale * 70368744177664.0f : p.scale;      // biased block carries power * 2^-46
-        ctx.scale[1] = p.scale;
+        const size_t tstride = (size_t)g.n_chan * p.n_beams;      // floats between consecutive output times
+        ctx.pair_stride = 2 * tstride;
+        ctx.scale = p.scale;
         uint32_t acc_cnt = 0;
+        int f = item_begin / g.n_tiles, t = item_begin - f * g.n_tiles - 1;   // advanced incrementally: no division per item
 #pragma unroll 1
         for (int item = item_begin; item < item_end; item++) {
-            const int f = item / g.n_tiles, t = item - f * g.n_tiles;
-            const int c0 = t * kTileN + col_b0, c1 = t * kTileN + col_b1;   // first global column of the two blocks
-            // valid groups per block (ragged last tile), pre-biased by the lane's own offset
-            const int left0 = g.n_cols_total - c0, left1 = g.n_cols_total - c1;
-            if (G == 64) {
-                ctx.vg[0] = (left0 >= 64) ? 1 : 0;
-                ctx.vg[1] = 0;
-            } else {
-                ctx.vg[0] = (left0 >= 32 ? kGpb : (left0 > 0 ? left0 / G : 0)) - (kLaneOff ? ctx.lane_odd : 0);
-                ctx.vg[1] = (left1 >= 32 ? kGpb : (left1 > 0 ? left1 / G : 0)) - (kLaneOff ? ctx.lane_odd : 0);
-            }
-            const size_t beam_off = (size_t)f * p.n_beams + (row >> 1);
-            size_t off0 = ((size_t)(c0 / G) + (kLaneOff ? ctx.lane_odd : 0)) * ctx.tstride + beam_off;
-            size_t off1 = ((size_t)(c1 / G) + (kLaneOff ? ctx.lane_odd : 0)) * ctx.tstride + beam_off;
-            asm volatile("" : "+l"(off0), "+l"(off1));               // keep live; do not recompute per M-tile
+            if (++t == g.n_tiles) { t = 0; f++; }
+            const int colbase = t * kTileN + wc * kEpiCols;          // first global column of this warp
+            const int cols_left = g.n_cols_total - colbase;
+            ctx.vg_lane = (cols_left >= kEpiCols ? kGroups : (cols_left > 0 ? cols_left / G : 0)) - ctx.lane_odd;
+            // even lanes (re rows) store the even group of each pair, odd lanes the odd group
+            const size_t out_off = ((size_t)(colbase / G) + ((kGroups > 1) ? ctx.lane_odd : 0)) * tstride + (size_t)f * p.n_beams + (row >> 1);
+            float *out_item = p.out + out_off;
+            asm volatile("" : "+l"(out_item));                       // keep the pointer live; do not recompute per M-tile
+            long long *pp_item = (EXACT && p.pdump) ? p.pdump + out_off : nullptr;
 #pragma unroll 1
             for (int m = 0; m < mt; m++, acc_cnt++) {
                 const uint32_t as = acc_cnt & 1;
@@ -455,11 +396,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 if (trc) p.trace[trb + 1] = clock64();
                 const uint32_t taddr = tbase_w + as * kAccCols;
                 uint32_t va[32], vb[32];
-                tmem_ld_32x32(taddr + col_b0, va);
-                tmem_ld_32x32(taddr + col_b1, vb);
+                tmem_ld_32x32(taddr, va);
+                tmem_ld_32x32(taddr + 32, vb);
                 tmem_ld_wait(va);
                 tmem_ld_wait(vb);
-                // both blocks are in registers: hand the TMEM stage back to the MMA right away
+                // both halves are in registers: hand the TMEM stage back to the MMA right away
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
@@ -475,19 +416,19 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                     const size_t cs = (size_t)p.n_beams * 2;
 #pragma unroll
                     for (int jj = 0; jj < 32; jj++) {
-                        if (c0 + jj < g.n_cols_total) vd[(size_t)(c0 + jj) * cs] = (int)va[jj] - (kMixed ? kBias : 0);
-                        if (c1 + jj < g.n_cols_total) vd[(size_t)(c1 + jj) * cs] = (int)vb[jj];
+                        if (colbase + jj < g.n_cols_total) vd[(size_t)(colbase + jj) * cs] = ((int)va[jj]) >> 4;
+                        if (colbase + 32 + jj < g.n_cols_total) vd[(size_t)(colbase + 32 + jj) * cs] = ((int)vb[jj]) >> 4;
                     }
                 }
                 ctx.acc.zero();
                 ctx.pend = 0;
-                ctx.op[0] = p.out + off0 + m * 64;                   // M-tile m = beams [64m, 64m+64)
-                ctx.op[1] = p.out + off1 + m * 64;
-                ctx.pp[0] = (EXACT && p.pdump) ? p.pdump + off0 + m * 64 : nullptr;
-                ctx.pp[1] = (EXACT && p.pdump) ? p.pdump + off1 + m * 64 : nullptr;
-                epi_block<G, EXACT, 0, kMixed>(ctx, va);
-                epi_block<G, EXACT, 1, false>(ctx, vb);
+                ctx.op = out_item;
+                ctx.pp = pp_item;
+                epi_block<G, EXACT, 0>(ctx, va);
+                epi_block<G, EXACT, 1>(ctx, vb);
                 if (trc) p.trace[trb + 3] = clock64();
+                out_item += 64;                                      // next M-tile = next 64 beams
+                if (EXACT) { if (pp_item) pp_item += 64; }
             }
         }
     }

@@ -153,17 +153,6 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr)
     d |= (uint64_t)2 << 61;
     return d;
 }
-// K-major, no-swizzle descriptor (canonical 8-row x 16-byte core matrices, 128 B each):
-// LBO = 128 B between core matrices adjacent in K, SBO = 256 B between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc_k_nosw(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(128 >> 4) << 16;
-    d |= (uint64_t)(256 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
 // kind::i8 instruction descriptor: D=S32 (2<<4), A=B=signed int8 (1<<7, 1<<10),
 // both K-major, N>>3 at bit 17, M>>4 at bit 24.
 __host__ __device__ constexpr uint32_t make_idesc_i8(uint32_t M, uint32_t N)
