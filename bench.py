@@ -142,6 +142,65 @@ class ClockSampler:
         return out
 
 
+
+def reference_gpu_baseline(tmpdir):
+    """The reference's own GPU sequence (expand_input -> cublasGemmStridedBatchedEx -> detect_sum) rebuilt for sm_100
+    (oracle/_ref/ref_kernels_obs, built from /root/reference by oracle/Makefile), timed by its own CUDA events on this GPU.
+    A reported baseline, not the target.  Returns None if the binary did not travel."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_kernels_obs")
+    if not os.path.exists(exe):
+        return None
+    rng = np.random.default_rng(7)
+    w = rng.integers(-127, 128, size=(N_CHAN, N_ANT, N_BEAMS, 2), dtype=np.int8)
+    x = rng.integers(0, 256, size=(2, N_CHAN, 256, N_ANT), dtype=np.uint8)
+    wf, xf = os.path.join(tmpdir, "w.i8"), os.path.join(tmpdir, "x.u8")
+    w.tofile(wf); x.tofile(xf)
+    try:
+        r = subprocess.run([exe, wf, xf, "2", os.path.join(tmpdir, "ref"), "40"], capture_output=True, text=True, timeout=300)
+    except (OSError, subprocess.TimeoutExpired):
+        return None
+    ms = {}
+    for line in r.stdout.splitlines():
+        parts = line.split()
+        if len(parts) == 2 and parts[0].startswith("ref_ms_per_chunk"):
+            ms[parts[0]] = float(parts[1])
+    if not ms or "gemm_status 0" not in r.stdout:
+        return None
+    best = min(ms.values())
+    samples_per_chunk = N_BEAMS * N_CHAN * 8 * N_AVG
+    return {"samples_per_s": samples_per_chunk / (best * 1e-3), "ms_per_chunk_1_stream": ms.get("ref_ms_per_chunk"),
+            "ms_per_chunk_8_streams": ms.get("ref_ms_per_chunk_8streams"),
+            "what": "reference kernels + cuBLAS 12.9 C8I GEMM rebuilt with -arch=sm_100, device-resident, per 4 MiB chunk"}
+
+
+def debug_shape_workload(bf, torch, device, weights):
+    """BASELINE.json configs[1]-style shape (DEBUG build: N_AVERAGING = 1, 16 columns per chunk, 2 MiB of float power out
+    per 256 KiB in): HBM-bound.  4096 chunks (= the 4096 grid sources) per launch, device-resident."""
+    B = bf.Beamformer(debug=True, device=device, exact_power=0)
+    B.set_weights(weights)
+    n_chunks = 4096
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        x = torch.randint(0, 256, (n_chunks * B.chunk_bytes,), dtype=torch.uint8, device="cuda")
+        out = torch.empty(n_chunks * B.chunk_out_floats, dtype=torch.float32, device="cuda")
+        for _ in range(2):
+            B.beamform_device(x.data_ptr(), n_chunks, out.data_ptr(), st.cuda_stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        reps = 5
+        for _ in range(reps):
+            B.beamform_device(x.data_ptr(), n_chunks, out.data_ptr(), st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    byts = n_chunks * (B.chunk_bytes + B.chunk_out_floats * 4)
+    samples = N_BEAMS * N_CHAN * n_chunks * 8
+    launches = B.kernel_launches
+    B.close()
+    del x, out
+    return {"workload": "DEBUG shape (N_AVERAGING=1): 4096 chunks of 262144 B, 256 ch x 256 beams (configs[1] shape)", "ms_per_launch": ms,
+            "samples_per_s": samples / (ms * 1e-3), "hbm_gb_s_algorithmic": byts / ms * 1e-6, "bound": "hbm"}, launches
+
 def run_ours(args):
     import torch
     import dsabeamformer_b200 as bf
@@ -275,6 +334,11 @@ def run_ours(args):
         except (OSError, ValueError, KeyError):
             pass
         cpu_v, cpu_s, cores = cpu_numpy_baseline(4096, repeats=5)
+        with tempfile.TemporaryDirectory() as td:
+            ref_gpu = reference_gpu_baseline(td)
+        dbg, dbg_launches = debug_shape_workload(bf, torch, local_rank, bf.compute_weights(pos, dirs, gpu=rank % 8))
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        dbg["frac_of_measured_hbm"] = dbg["hbm_gb_s_algorithmic"] / hbm_peak
         line = {
             "metric": "beamformed samples/s (beams x chans x input-time)", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
@@ -295,6 +359,8 @@ def run_ours(args):
             "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": "4096 columns (2048 input times x 2 pol) x 256 channels, numpy complex128 matmul per channel, best of 5 passes of %.1f s" % cpu_s},
             "clocks": clocks,
+            "reference_gpu_sm100": ref_gpu,
+            "other_workloads": [dbg],
             "x_realtime_per_gpu": value / world / REALTIME_SAMPLES_PER_S,
             "int8_tops": value * OPS_PER_SAMPLE * 1e-12,
         }

@@ -66,6 +66,7 @@ struct __align__(1024) Smem {
     uint64_t b_full[2], b_empty[2];
     uint64_t a_full[kMaxMT], a_empty[kMaxMT];
     uint64_t acc_full[2], acc_empty[2];
+    uint32_t acc_arrivals[2];            // epilogue warps that have drained a TMEM stage (the last one signals acc_empty)
     uint32_t tmem_base;
 };
 
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
             for (int item = item_begin, it = 0; item < item_end; item++, it++) {
                 const int f = item / g.n_tiles, t = item - f * g.n_tiles;
                 const int s = it % kStages;
-                mbar_wait(bar_stg_empty + 8 * s, ((it / kStages) & 1) ^ 1, 1);
+                mbar_wait<1000>(bar_stg_empty + 8 * s, ((it / kStages) & 1) ^ 1, 1);
                 const int col0 = t * kTileN;
                 if (g.cpc >= kTileN) {
                     const int chunk = col0 / g.cpc, c_in = col0 - chunk * g.cpc;
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 if (f == cur_f) continue;
                 cur_f = f;
                 for (int m = 0; m < mt; m++) {
-                    mbar_wait(bar_a_empty + 8 * m, (ch & 1) ^ 1, 2);
+                    mbar_wait<2000>(bar_a_empty + 8 * m, (ch & 1) ^ 1, 2);
                     mbar_arrive_expect_tx(bar_a_full + 8 * m, kATileBytes);
                     tma_bulk_g2s_hint(a_smem + m * kATileBytes, p.wprep + ((size_t)f * mt + m) * kATileBytes, kATileBytes, bar_a_full + 8 * m, pol);
                 }
@@ -334,9 +335,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
             const int s = it % kStages, buf = it & 1;
             const bool utr = p.trace && blockIdx.x == 0 && uw == 0 && lane == 0 && it < 32;
             if (utr) p.trace[it * 64 + 12] = clock64();
-            mbar_wait(bar_stg_full + 8 * s, (it / kStages) & 1, 6);
+            mbar_wait<200>(bar_stg_full + 8 * s, (it / kStages) & 1, 6);
             if (utr) p.trace[it * 64 + 13] = clock64();
-            mbar_wait(bar_b_empty + 8 * buf, ((it >> 1) & 1) ^ 1, 7);
+            mbar_wait<500>(bar_b_empty + 8 * buf, ((it >> 1) & 1) ^ 1, 7);
             if (utr) p.trace[it * 64 + 14] = clock64();
             const uint32_t src = stg_smem + s * kStageBytes + ld_off;
             const uint32_t dst = b_smem + buf * kBTileBytes;

@@ -231,12 +231,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// BACKOFF_NS > 0: sleep that long between probes.  For waits that are expected to be long (a slot
+// freed once per work item) -- a hinted try_wait alone wakes up at every arrival on the barrier and
+// the probing warp then competes for issue slots with the epilogue warps of its sub-partition.
+template <int BACKOFF_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0)
 {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = 0;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (BACKOFF_NS > 0) __nanosleep(BACKOFF_NS);
         if ((++spins & 255u) == 0) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
