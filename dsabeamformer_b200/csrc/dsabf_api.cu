@@ -11,6 +11,7 @@
 #include "fused_beamform.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -114,6 +115,7 @@ int run_fused(dsabf_handle *h, const uint8_t *d_packed, int n_chunks, float *d_o
     p.n_chunks = n_chunks;
     p.cols_per_chunk = h->cols_per_chunk;
     p.group = h->group;
+    p.n_ant = h->cfg.n_antennas;
     p.n_beams = h->cfg.n_beams;
     const long long cols = (long long)n_chunks * h->cols_per_chunk;
     p.n_tiles = (int)((cols + 255) / 256);
@@ -132,7 +134,10 @@ int run_fused(dsabf_handle *h, const uint8_t *d_packed, int n_chunks, float *d_o
         h->t_used++;
         CK(cudaEventRecord(e0, st));
     }
-    CK(dsabf::launch_fused_beamform(p, exact, h->num_sms, st));
+    // 64 antennas x <= 256 beams: weights resident per channel; anything larger: streamed-weights kernel
+    static const bool force_big = getenv("DSABF_FORCE_STREAMED") != nullptr;     // testing hook: route every shape through the streamed-weights kernel
+    if (h->cfg.n_antennas == 64 && h->cfg.n_beams <= 256 && !force_big) CK(dsabf::launch_fused_beamform(p, exact, h->num_sms, st));
+    else CK(dsabf::launch_fused_beamform_big(p, exact, h->num_sms, st));
     if (e1) CK(cudaEventRecord(e1, st));
     h->launches++;
     return 0;
@@ -170,8 +175,8 @@ int dsabf_create(const dsabf_config *cfg, dsabf_handle **out)
 {
     if (!cfg || !out) return fail(DSABF_E_INVALID, "NULL argument");
     *out = nullptr;
-    if (cfg->n_antennas != 64) return fail(DSABF_E_INVALID, "n_antennas must be 64 in this build");
-    if (cfg->n_beams < 64 || cfg->n_beams > 256 || cfg->n_beams % 64) return fail(DSABF_E_INVALID, "n_beams must be 64, 128, 192 or 256");
+    if (cfg->n_antennas < 64 || cfg->n_antennas > 256 || cfg->n_antennas % 64) return fail(DSABF_E_INVALID, "n_antennas must be 64, 128, 192 or 256");
+    if (cfg->n_beams < 64 || cfg->n_beams > 4096 || cfg->n_beams % 64) return fail(DSABF_E_INVALID, "n_beams must be a multiple of 64 in [64, 4096]");
     if (cfg->n_channels < 1) return fail(DSABF_E_INVALID, "n_channels must be >= 1");
     if (cfg->n_pol < 1 || cfg->n_averaging < 1) return fail(DSABF_E_INVALID, "n_pol, n_averaging must be >= 1");
     const int group = cfg->n_pol * cfg->n_averaging;

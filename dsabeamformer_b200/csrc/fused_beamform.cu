@@ -29,34 +29,15 @@
 //   warps 12-15 unpack: staging -> sign-preserving nibble split -> SW128 K-major B' tile
 // Voltages are read from HBM once, weights once per (CTA, channel); nothing but
 // the final float power is written.
-#include "fused_beamform.cuh"
-#include "sm100_ptx.cuh"
-#include <cstddef>
-#include <type_traits>
+#include "fused_epilogue.cuh"
 
 namespace dsabf {
 
 using namespace ptx;
+using namespace fused;
 
 namespace {
 
-constexpr int kTileN = 256;              // columns per work item (UMMA N)
-constexpr int kRowBytes = 128;           // K' bytes per row = 2 * 64 antennas
-constexpr int kATileBytes = 128 * kRowBytes;   // 16 KB: one M=128 weights tile
-constexpr int kBTileBytes = kTileN * kRowBytes; // 32 KB: unpacked voltages tile
-constexpr int kStageBytes = kTileN * 64;        // 16 KB: packed voltages tile
-constexpr int kStages = 4;
-constexpr int kMaxMT = 4;
-constexpr int kAccCols = 256;            // TMEM columns per accumulator stage
-constexpr int kTmemCols = 512;
-
-// warp roles: warpgroup 0 = {TMA, MMA, weights+TMEM alloc, idle}, warpgroup 1 = unpack,
-// warpgroups 2-5 = epilogue (16 warps: TMEM lane quarter = warp % 4, 64 columns each)
-constexpr int kUnpackWarp0 = 4, kNumUnpackWarps = 4;
-constexpr int kEpiWarp0 = 8, kNumEpiWarps = 16;
-constexpr int kThreads = (kEpiWarp0 + kNumEpiWarps) * 32;   // 768
-constexpr int kEpiCols = kTileN / (kNumEpiWarps / 4);       // 64 columns per epilogue warp
-constexpr int kRegsLight = 40, kRegsEpi = 96;               // setmaxnreg budgets (launch: 80)
 
 struct __align__(1024) Smem {
     uint8_t a[kMaxMT][kATileBytes];      // 64 KB  resident weights of the current channel
@@ -66,129 +47,8 @@ struct __align__(1024) Smem {
     uint64_t b_full[2], b_empty[2];
     uint64_t a_full[kMaxMT], a_empty[kMaxMT];
     uint64_t acc_full[2], acc_empty[2];
-    uint32_t acc_arrivals[2];            // epilogue warps that have drained a TMEM stage (the last one signals acc_empty)
     uint32_t tmem_base;
 };
-
-// Square-accumulate of one row's voltages in the two supported arithmetic modes.
-// Both keep several independent partial sums so that consecutive columns do not
-// form one long dependent chain.
-//  EXACT : int64 via mad.wide.s32 (IMAD.WIDE) -- integer power exact, slower.
-//  fast  : fp32; two columns at a time are converted (I2FP) and fed to one packed
-//          fma.rn.f32x2 (FFMA2).  Exact whenever the integer power is < 2^24
-//          (every partial sum is then an exactly representable integer multiple
-//          of 256); otherwise <= G * 2^-24 relative, ~1e-7 typical.
-template <bool EXACT> struct Acc;
-template <> struct Acc<true> {
-    using sum_t = long long;
-    long long s0, s1, s2, s3;
-    __device__ __forceinline__ void zero() { s0 = s1 = s2 = s3 = 0; }
-    template <int SLOT> __device__ __forceinline__ void add2(int v0, int v1)
-    {
-        if (SLOT == 0) {
-            asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s0) : "r"(v0));
-            asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s1) : "r"(v1));
-        } else {
-            asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s2) : "r"(v0));
-            asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s3) : "r"(v1));
-        }
-    }
-    // sum of the first NSLOT packed slots that were used since zero()
-    template <int NSLOT> __device__ __forceinline__ long long sum() const { return NSLOT == 1 ? (s0 + s1) : (s0 + s1) + (s2 + s3); }
-};
-template <> struct Acc<false> {
-    using sum_t = float;
-    unsigned long long a0, a1;     // two packed float2 accumulators
-    __device__ __forceinline__ void zero() { a0 = 0ull; a1 = 0ull; }
-    template <int SLOT> __device__ __forceinline__ void add2(int v0, int v1)
-    {
-        float f0, f1;
-        asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f0) : "r"(v0));
-        asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f1) : "r"(v1));
-        if (SLOT == 0) asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a0) : "f"(f0), "f"(f1));
-        else           asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a1) : "f"(f0), "f"(f1));
-    }
-    template <int NSLOT> __device__ __forceinline__ float sum() const
-    {
-        float a, b, c, d;
-        asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(a0));
-        if (NSLOT == 1) return a + b;
-        asm("mov.b64 {%0, %1}, %2;" : "=f"(c), "=f"(d) : "l"(a1));
-        return (a + b) + (c + d);
-    }
-};
-
-// Work-item geometry shared by all roles.
-struct Geom {
-    int n_chan, n_chunks, cpc, n_tiles, n_cols_total;
-    __device__ __forceinline__ Geom(const FusedParams &p)
-        : n_chan(p.n_chan), n_chunks(p.n_chunks), cpc(p.cols_per_chunk), n_tiles(p.n_tiles),
-          n_cols_total(p.n_chunks * p.cols_per_chunk) {}
-};
-
-// Per-(row, M-tile) epilogue state of one thread.
-template <bool EXACT> struct EpiCtx {
-    using sum_t = typename Acc<EXACT>::sum_t;
-    Acc<EXACT> acc;       // running sum of squares of the current group of G columns
-    sum_t pend;           // finished even group waiting for the odd group of its pair
-    int lane_odd;         // odd lanes hold im rows
-    int vg_lane;          // (valid groups of this warp's 64 columns) - lane_odd   (ragged last tile)
-    float *op;            // running pointer: &out[next group pair + lane_odd][f][beam of this row]
-    long long *pp;        // same for the exact-power dump (nullptr = off)
-    size_t pair_stride;   // elements between consecutive group pairs = 2 output times
-    float scale;
-};
-
-// Store the finished output of group pair PAIR (compile-time) and advance the pointers.
-template <bool EXACT>
-__device__ __forceinline__ void epi_store(EpiCtx<EXACT> &c, typename EpiCtx<EXACT>::sum_t tot, int first_grp_of_pair)
-{
-    if (first_grp_of_pair < c.vg_lane) {
-        *c.op = (float)tot * c.scale;
-        if (EXACT) {
-            if (c.pp) *c.pp = (long long)tot >> 8;
-        }
-    }
-    c.op += c.pair_stride;
-    if (EXACT) {
-        if (c.pp) c.pp += c.pair_stride;
-    }
-}
-
-// 32 accumulator columns [BLK*32, BLK*32+32) of this warp's 64: square, sum per
-// group of G columns, and on every second finished group exchange with the lane
-// holding the other component (re rows = even lanes, im rows = odd lanes): even
-// lanes finish the even group of the pair, odd lanes the odd group, so one
-// shuffle yields two outputs and a warp stores 2 x 64 contiguous bytes.
-template <int G, bool EXACT, int BLK>
-__device__ __forceinline__ void epi_block(EpiCtx<EXACT> &c, const uint32_t (&v)[32])
-{
-    constexpr int kGroups = kEpiCols / G;                 // groups per warp: 32,16,8,4,2,1
-    constexpr int kSlots = (G >= 4) ? 2 : 1;              // packed accumulator slots in use
-#pragma unroll
-    for (int jj = 0; jj < 32; jj += 2) {
-        if (kSlots == 1 || ((jj >> 1) & 1) == 0) c.acc.template add2<0>((int)v[jj], (int)v[jj + 1]);
-        else                                     c.acc.template add2<1>((int)v[jj], (int)v[jj + 1]);
-        const int cl = BLK * 32 + jj + 1;          // last column handled so far (compile-time after unrolling)
-        if (((cl + 1) % G) == 0) {
-            const int grp = cl / G;
-            const auto sgrp = c.acc.template sum<kSlots>();
-            c.acc.zero();
-            if (kGroups == 1) {
-                const auto tot = sgrp + __shfl_xor_sync(0xffffffffu, sgrp, 1);
-                // single group: only the even lanes (vg_lane = valid - 0) store
-                if (!c.lane_odd) epi_store<EXACT>(c, tot, 0);
-            } else if ((grp & 1) == 0) {
-                c.pend = sgrp;
-            } else {
-                const auto send = c.lane_odd ? c.pend : sgrp;
-                const auto mine = c.lane_odd ? sgrp : c.pend;
-                const auto tot = mine + __shfl_xor_sync(0xffffffffu, send, 1);
-                epi_store<EXACT>(c, tot, grp - 1);
-            }
-        }
-    }
-}
 
 // MODE: 0 = fast fp32 power, 1 = exact int64 power (+ optional integer-power dump),
 //       2 = exact + int32 voltage dump (debug / parity tap)
@@ -472,7 +332,7 @@ cudaError_t launch_g(const FusedParams &p, int grid, cudaStream_t stream)
 
 cudaError_t launch_fused_beamform(const FusedParams &p, bool exact, int num_sms, cudaStream_t stream)
 {
-    if (p.n_beams % 64 || p.n_beams < 64 || p.n_beams > 64 * kMaxMT) return cudaErrorInvalidValue;
+    if (p.n_ant != 64 || p.n_beams % 64 || p.n_beams < 64 || p.n_beams > 64 * kMaxMT) return cudaErrorInvalidValue;
     if (p.cols_per_chunk % p.group) return cudaErrorInvalidValue;
     if (!((p.cols_per_chunk >= kTileN && p.cols_per_chunk % kTileN == 0) || (kTileN % p.cols_per_chunk == 0)))
         return cudaErrorInvalidValue;
@@ -490,32 +350,34 @@ cudaError_t launch_fused_beamform(const FusedParams &p, bool exact, int num_sms,
 __global__ void prep_weights_kernel(const int8_t *__restrict__ w, uint8_t *__restrict__ wprep, int n_chan, int n_ant, int n_beams,
                                     int *__restrict__ bad)
 {
-    const int mt = n_beams >> 6;
-    const size_t total = (size_t)n_chan * mt * 128 * 128;
+    const int mt = n_beams >> 6, kbn = n_ant >> 6;
+    const size_t total = (size_t)n_chan * mt * kbn * 128 * 128;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int kb = idx & 127;                  // logical K byte
+        const int kbyte = idx & 127;               // logical K byte inside the k-block
         const int r = (idx >> 7) & 127;            // row in the M tile
-        const size_t fm = idx >> 14;
+        const size_t tile = idx >> 14;             // ((f * mt) + m) * kbn + kb
+        const int kb = tile % kbn;
+        const size_t fm = tile / kbn;
         const int m = fm % mt;
         const int f = fm / mt;
         const int beam = m * 64 + (r >> 1);
         const int comp = r & 1;                    // 0: re row, 1: im row
-        const int a = kb & 63;
-        const int hi = kb >> 6;                    // 0: multiplies Xre, 1: multiplies Xim
+        const int a = kb * 64 + (kbyte & 63);      // antenna
+        const int hi = kbyte >> 6;                 // 0: multiplies Xre, 1: multiplies Xim
         const int8_t *wp = w + (((size_t)f * n_ant + a) * n_beams + beam) * 2;
         const int wre = wp[0], wim = wp[1];
         if (wre == -128 || wim == -128) *bad = 1;
         int val;
         if (comp == 0) val = hi ? -wim : wre;
         else           val = hi ? wre : wim;
-        const size_t off = fm * kATileBytes + (size_t)(r >> 3) * 1024 + (r & 7) * 128 + ((((kb >> 4) ^ (r & 7))) << 4) + (kb & 15);
+        const size_t off = tile * kATileBytes + (size_t)(r >> 3) * 1024 + (r & 7) * 128 + ((((kbyte >> 4) ^ (r & 7))) << 4) + (kbyte & 15);
         wprep[off] = (uint8_t)(int8_t)val;
     }
 }
 
 cudaError_t launch_prep_weights(const int8_t *d_w, uint8_t *d_wprep, int n_chan, int n_ant, int n_beams, int *d_bad, cudaStream_t stream)
 {
-    if (n_ant != 64) return cudaErrorInvalidValue;
+    if (n_ant % 64 || n_ant < 64 || n_ant > 256 || n_beams % 64) return cudaErrorInvalidValue;
     prep_weights_kernel<<<1184, 256, 0, stream>>>(d_w, d_wprep, n_chan, n_ant, n_beams, d_bad);
     return cudaGetLastError();
 }

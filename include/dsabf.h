@@ -44,8 +44,8 @@ typedef struct dsabf_handle dsabf_handle;
 /* Shape constants of /root/reference/src/beamformer.hh:47-60,108-147, made
  * run-time.  dsabf_default_config() fills in the reference's values. */
 typedef struct dsabf_config {
-    int n_antennas;           /* N_ANTENNAS 64 (this build: must be 64)                     */
-    int n_beams;              /* N_BEAMS 256   (multiple of 64, <= 256)                      */
+    int n_antennas;           /* N_ANTENNAS 64 (64, 128, 192 or 256)                        */
+    int n_beams;              /* N_BEAMS 256   (multiple of 64, <= 4096)                     */
     int n_channels;           /* N_FREQUENCIES 256 (any >= 1)                                */
     int n_pol;                /* N_POL 2                                                     */
     int n_averaging;          /* N_AVERAGING: 16 observation / 1 DEBUG (power of two <= 32) */

@@ -21,12 +21,12 @@ REL_TOL = 1e-6          # north_star tolerance for float power
 ALPHA2 = float(np.float32(1.0 / 127)) ** 2
 
 
-def _rand_case(bf, debug, n_chan, n_chunks, seed, n_beams=256, int4_full_range=True, **kw):
+def _rand_case(bf, debug, n_chan, n_chunks, seed, n_beams=256, n_ant=64, **kw):
     rng = np.random.default_rng(seed)
-    B = bf.Beamformer(debug=debug, n_channels=n_chan, n_beams=n_beams, **kw)
-    w = rng.integers(-127, 128, size=(n_chan, 64, n_beams, 2), dtype=np.int8)
+    B = bf.Beamformer(debug=debug, n_channels=n_chan, n_beams=n_beams, n_antennas=n_ant, **kw)
+    w = rng.integers(-127, 128, size=(n_chan, n_ant, n_beams, 2), dtype=np.int8)
     B.set_weights(w)
-    packed = rng.integers(0, 256, size=(n_chunks, n_chan, B.cols_per_chunk, 64), dtype=np.uint8)
+    packed = rng.integers(0, 256, size=(n_chunks, n_chan, B.cols_per_chunk, n_ant), dtype=np.uint8)
     return B, w, packed
 
 
@@ -66,6 +66,34 @@ def test_fewer_beams(bf, oracle, n_beams):
 def test_other_averaging_lengths(bf, oracle, navg):
     B, w, packed = _rand_case(bf, False, 2, 2 if navg < 32 else 1, seed=navg, n_averaging=navg)
     _check_against_oracle(oracle, B, w, packed, B.beamform(packed))
+    B.close()
+
+
+@pytest.mark.parametrize("n_ant,n_beams,debug,n_chan,n_chunks", [
+    (256, 2048, False, 2, 1),      # BASELINE.json configs[3] shape (scaled array), two channels of it
+    (256, 256, True, 3, 21),       # 4 k-blocks, DEBUG columns, ragged last tile
+    (128, 320, False, 2, 1),       # 2 k-blocks, odd number of M-tiles (the two MMA issuers alternate per item)
+    (64, 512, False, 3, 2),        # more beams than the resident-weights kernel holds
+    (192, 64, True, 2, 16),        # single M-tile: one issuer per item
+])
+def test_streamed_weights_kernel_matches_oracle(bf, oracle, n_ant, n_beams, debug, n_chan, n_chunks):
+    """fused_beamform_big.cu: up to 256 antennas / 4096 beams (weights streamed through shared memory)."""
+    B, w, packed = _rand_case(bf, debug, n_chan, n_chunks, seed=n_ant + n_beams, n_beams=n_beams, n_ant=n_ant)
+    _check_against_oracle(oracle, B, w, packed, B.beamform(packed))
+    B.close()
+
+
+def test_scaled_array_worst_case_voltage(bf, oracle):
+    """256 antennas, every sample -8-8j, weights +-127: |V| = 4 * 130048 (x16 inside the kernel: < 2^23)."""
+    B = bf.Beamformer(debug=False, n_channels=1, n_antennas=256, n_beams=128)
+    w = np.full((1, 256, 128, 2), 127, dtype=np.int8)
+    w[0, :, ::2, 1] = -127
+    B.set_weights(w)
+    packed = np.full((1, 1, 256, 256), 0x88, dtype=np.uint8)
+    V, P = B.voltages(packed)
+    Vo = oracle.beamform(packed[0], w)
+    assert np.array_equal(V, Vo) and np.abs(Vo).max() == 4 * 130048
+    assert np.array_equal(P, oracle.power_int(Vo, 32))
     B.close()
 
 
