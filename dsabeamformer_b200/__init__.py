@@ -15,7 +15,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libdsabf.so")
+LIB_PATH = os.environ.get("DSABF_LIB") or os.path.join(CSRC, "libdsabf.so")    # DSABF_LIB: developer hook for instrumented builds
 
 E_INVALID, E_STATE, E_WEIGHT = 10001, 10002, 10003
 

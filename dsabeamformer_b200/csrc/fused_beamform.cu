@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
             mbar_init(&sm.b_full[i], kNumUnpackWarps); mbar_init(&sm.b_empty[i], (p.n_beams >> 6) == 1 ? 1 : 2);   // one commit per MMA issuer
             mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps);
         }
-        for (int i = 0; i < kMaxMT; i++) { mbar_init(&sm.a_full[i], 1); mbar_init(&sm.a_empty[i], 1); }
+        for (int i = 0; i < kMaxMT; i++) { mbar_init(&sm.a_full[i], 1); mbar_init(&sm.a_empty[i], 2); }   // both issuers release a weight tile
         fence_mbar_init();
     }
     if (warp == 2) { tmem_alloc(&sm.tmem_base, kTmemCols); tmem_relinquish(); }
@@ -147,10 +147,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
             constexpr uint32_t idesc = make_idesc_i8(128, kTileN);
             int cur_f = -1, ch = -1;
             uint32_t acc_cnt = 0, use = 0;          // use: how often this issuer's stage has been filled
+            uint32_t seen = 0, released = 0;        // weight tiles of the current channel this issuer has seen arrive / has released
             for (int item = item_begin, it = 0; item < item_end; item++, it++) {
                 const int f = item / g.n_tiles;
                 const bool new_ch = (f != cur_f);
-                if (new_ch) { cur_f = f; ch++; }
+                if (new_ch) { cur_f = f; ch++; seen = 0; released = 0; }
                 const bool last_of_ch = (item + 1 == item_end) || ((item + 1) / g.n_tiles != f);
                 const int buf = it & 1;
                 bool touched = false;
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                         bdesc = make_desc_k_sw128(b_smem + buf * kBTileBytes);
                         touched = true;
                     }
-                    if (new_ch) mbar_wait(bar_a_full + 8 * m, ch & 1, 4);
+                    if (!((seen >> m) & 1u)) { mbar_wait(bar_a_full + 8 * m, ch & 1, 4); seen |= 1u << m; }
                     const long long tr0 = p.trace ? clock64() : 0;
                     mbar_wait(bar_acc_empty + 8 * me, (use & 1) ^ 1, 5);
                     tc_fence_after();
@@ -174,10 +175,21 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                         mma_i8_ss(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0);
                     tc_commit(bar_acc_full + 8 * me);
                     if (p.trace && blockIdx.x == 0 && acc_cnt < 128) p.trace[acc_cnt * 16 + 2] = clock64();
-                    if (last_of_ch) tc_commit(bar_a_empty + 8 * m);
+                    if (last_of_ch) { tc_commit(bar_a_empty + 8 * m); released |= 1u << m; }
                     use++;
                 }
                 if (touched) tc_commit(bar_b_empty + 8 * buf);
+                // A parity wait cannot tell "this phase is done" from "the previous one is not yet", so a waiter has
+                // to observe every phase of a barrier, at most one phase late.  Both issuers therefore wait for and
+                // release every weight tile of every channel -- also the tiles the other issuer multiplied -- and
+                // the loader refills a tile only after both releases (a_empty counts 2).
+                if (last_of_ch) {
+                    for (int m = 0; m < mt; m++) {
+                        if ((released >> m) & 1u) continue;
+                        if (!((seen >> m) & 1u)) mbar_wait(bar_a_full + 8 * m, ch & 1, 4);
+                        tc_commit(bar_a_empty + 8 * m);
+                    }
+                }
             }
         }
     } else if (warp < kEpiWarp0) {

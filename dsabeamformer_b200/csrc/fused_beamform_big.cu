@@ -23,7 +23,14 @@ using namespace fused;
 namespace {
 
 constexpr int kMaxKB = 4;      // k-blocks of 64 antennas
-constexpr int kARing = 5;      // weight tiles in flight
+// Weight tiles in flight: one ring, filled in stream order by the loader and drained by the two MMA
+// issuers, which alternate M-tile by M-tile.  TMA loads complete out of order and an mbarrier parity wait
+// cannot tell "round R is done" from "round R-1 is not", so a waiter must never ask for round R of a slot
+// before round R-1 has completed.  With two consumers that needs the baton below (turn[]): an issuer starts
+// waiting for the tiles of M-tile a only after the other issuer has seen every tile of M-tile a-1 arrive.
+// (Without it issuer B could run ahead on a stale slot, release it, and the loader would re-arm a barrier
+// whose transaction is still pending -- an illegal-instruction trap under load.)
+constexpr int kARing = 6;
 // Register budgets (setmaxnreg).  The CTA owns 768 x 80 registers; after redistribution the sum must not
 // exceed that, or the last setmaxnreg.inc waits forever:  4 light warps x 32 + 4 unpack warps x 64 +
 // 16 epilogue warps x 96 = 480 x 128 = 768 x 80 exactly.
@@ -32,13 +39,15 @@ constexpr int kRegsUnpackBig = 64;
 static_assert(4 * kRegsLightBig + 4 * kRegsUnpackBig + 16 * kRegsEpi <= 24 * 80, "setmaxnreg budget exceeds the CTA's allocation");
 
 struct __align__(1024) SmemBig {
-    uint8_t a[kARing][kATileBytes];      //  80 KB  streamed weight tiles
+    uint8_t a[kARing][kATileBytes];      //  96 KB  streamed weight tiles
     uint8_t b[kMaxKB][kBTileBytes];      // 128 KB  unpacked voltages of the current item, one tile per k-block
     uint64_t a_full[kARing], a_empty[kARing];
     uint64_t b_full, b_empty;
     uint64_t acc_full[2], acc_empty[2];
+    uint64_t turn[2];                    // baton between the two MMA issuers
     uint32_t tmem_base;
 };
+static_assert(sizeof(SmemBig) + 1024 <= 232448, "SmemBig exceeds the 227 KB a CTA can opt in to");
 
 __device__ __forceinline__ uint4 ldg128_stream(const void *p)
 {
@@ -70,7 +79,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
         for (int i = 0; i < kARing; i++) { mbar_init(&sm.a_full[i], 1); mbar_init(&sm.a_empty[i], 1); }
         mbar_init(&sm.b_full, kNumUnpackWarps);
         mbar_init(&sm.b_empty, mt == 1 ? 1 : 2);                 // one commit per MMA issuer
-        for (int i = 0; i < 2; i++) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps); }
+        for (int i = 0; i < 2; i++) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps); mbar_init(&sm.turn[i], 1); }
         fence_mbar_init();
     }
     if (warp == 2) { tmem_alloc(&sm.tmem_base, kTmemCols); tmem_relinquish(); }
@@ -83,40 +92,46 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
     const uint32_t bar_a_full = sbase + (uint32_t)offsetof(SmemBig, a_full), bar_a_empty = sbase + (uint32_t)offsetof(SmemBig, a_empty);
     const uint32_t bar_b_full = sbase + (uint32_t)offsetof(SmemBig, b_full), bar_b_empty = sbase + (uint32_t)offsetof(SmemBig, b_empty);
     const uint32_t bar_acc_full = sbase + (uint32_t)offsetof(SmemBig, acc_full), bar_acc_empty = sbase + (uint32_t)offsetof(SmemBig, acc_empty);
+    const uint32_t bar_turn = sbase + (uint32_t)offsetof(SmemBig, turn);
 
     if (warp < kUnpackWarp0) {
         setmaxnreg_dec<kRegsLightBig>();
         if (warp == 0 && lane == 0) {
-            // ================= weights loader: stream (item, M-tile, k-block) through the ring =================
+            // ================= weights loader: stream (item, M-tile, k-block) into the issuers' rings =================
             const uint64_t pol = policy_evict_last();
-            uint32_t q = 0;
+            uint32_t q = 0;                                      // position in the weight stream
             for (int item = item_begin; item < item_end; item++) {
                 const int f = item / g.n_tiles;
                 const uint8_t *wf = p.wprep + (size_t)f * mt * kb_n * kATileBytes;
-                for (int mk = 0; mk < mt * kb_n; mk++, q++) {
+                for (int mk = 0; mk < mt * kb_n; mk++, q++, wf += kATileBytes) {
                     const uint32_t slot = q % kARing;
                     mbar_wait<100>(bar_a_empty + 8 * slot, ((q / kARing) & 1) ^ 1, 2);
                     mbar_arrive_expect_tx(bar_a_full + 8 * slot, kATileBytes);
-                    tma_bulk_g2s_hint(a_smem + slot * kATileBytes, wf + (size_t)mk * kATileBytes, kATileBytes, bar_a_full + 8 * slot, pol);
+                    tma_bulk_g2s_hint(a_smem + slot * kATileBytes, wf, kATileBytes, bar_a_full + 8 * slot, pol);
                 }
             }
         } else if ((warp == 1 || warp == 3) && lane == 0) {
             // ================= MMA issuers (one per TMEM accumulator stage) =================
             const int me = (warp == 3) ? 1 : 0;
             constexpr uint32_t idesc = make_idesc_i8(128, kTileN);
-            uint32_t acc_cnt = 0, use = 0;
+            uint32_t acc_cnt = 0, use = 0;                       // use: M-tiles this issuer has multiplied
             for (int item = item_begin, it = 0; item < item_end; item++, it++) {
+                // every issuer observes every phase of b_full, also for an item it has no M-tile of (n_beams = 64)
+                mbar_wait(bar_b_full, it & 1, 3);
                 bool touched = false;
                 for (int m = 0; m < mt; m++, acc_cnt++) {
                     if ((int)(acc_cnt & 1) != me) continue;
-                    if (!touched) { mbar_wait(bar_b_full, it & 1, 3); touched = true; }
+                    touched = true;
                     mbar_wait(bar_acc_empty + 8 * me, (use & 1) ^ 1, 5);
+                    // baton: the other issuer has seen all tiles of M-tile acc_cnt-1 land
+                    if (acc_cnt > 0) mbar_wait(bar_turn + 8 * me, (me ? use : use - 1) & 1, 6);
                     tc_fence_after();
                     const uint32_t d = tmem_base + me * kAccCols;
                     for (int kb = 0; kb < kb_n; kb++) {
-                        const uint32_t q = acc_cnt * kb_n + kb;        // position in the weight stream
+                        const uint32_t q = acc_cnt * kb_n + kb;
                         const uint32_t slot = q % kARing;
                         mbar_wait(bar_a_full + 8 * slot, (q / kARing) & 1, 4);
+                        if (kb == kb_n - 1) mbar_arrive(bar_turn + 8 * (me ^ 1));      // pass the baton
                         tc_fence_after();
                         const uint64_t adesc = make_desc_k_sw128(a_smem + slot * kATileBytes);
                         const uint64_t bdesc = make_desc_k_sw128(b_smem + kb * kBTileBytes);

@@ -249,6 +249,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
         }
     }
 }
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t smem_dst, const void *gmem_src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gmem_src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_bulk_g2s_hint(uint32_t smem_dst, const void *gmem_src, uint32_t bytes, uint32_t bar, uint64_t policy)
 {
     asm volatile(

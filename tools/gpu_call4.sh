@@ -1,4 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q --durations=8 2>&1 | tail -14
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_beamform -s 2 -c 1 -f -o gpurun_out/prof_obs2 python tools/prof_one.py obs 0 4 2>&1 | tail -2
+for s in "256 2048 256 8" "256 2048 256 32" "128 1024 256 32" "64 512 256 32" "256 256 256 32" "64 256 256 32"; do
+  timeout 120 python tools/time_shape.py $s 2>&1 | tail -1
+done | tee gpurun_out/time_shapes.txt
+echo forced; DSABF_FORCE_STREAMED=1 timeout 120 python tools/time_shape.py 64 256 256 32 | tee -a gpurun_out/time_shapes.txt
