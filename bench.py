@@ -201,6 +201,37 @@ def debug_shape_workload(bf, torch, device, weights):
     return {"workload": "DEBUG shape (N_AVERAGING=1): 4096 chunks of 262144 B, 256 ch x 256 beams (configs[1] shape)", "ms_per_launch": ms,
             "samples_per_s": samples / (ms * 1e-3), "hbm_gb_s_algorithmic": byts / ms * 1e-6, "bound": "hbm"}, launches
 
+def scaled_array_workload(bf, torch, device):
+    """BASELINE.json configs[3], one GPU's share of the frequency-sharded scaled array: 256 antennas x 2048 beams x
+    256 channels, one 32-chunk block (8192 columns, 512 MiB in / 512 MiB out), device-resident, random int8 weights
+    (streamed-weights kernel, fused_beamform_big.cu): tensor-bound."""
+    import numpy as np
+    n_ant, n_beams, n_chan, n_chunks = 256, 2048, 256, 32
+    B = bf.Beamformer(debug=False, device=device, n_antennas=n_ant, n_beams=n_beams, n_channels=n_chan, exact_power=0)
+    B.set_weights(np.random.default_rng(3).integers(-127, 128, size=(n_chan, n_ant, n_beams, 2), dtype=np.int8))
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        x = torch.randint(0, 256, (n_chunks * B.chunk_bytes,), dtype=torch.uint8, device="cuda")
+        out = torch.empty(n_chunks * B.chunk_out_floats, dtype=torch.float32, device="cuda")
+        for _ in range(2):
+            B.beamform_device(x.data_ptr(), n_chunks, out.data_ptr(), st.cuda_stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        reps = 5
+        for _ in range(reps):
+            B.beamform_device(x.data_ptr(), n_chunks, out.data_ptr(), st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    cols = n_chunks * B.cols_per_chunk
+    samples = n_beams * n_chan * (cols // N_POL)
+    launches = B.kernel_launches
+    B.close()
+    del x, out
+    return {"workload": "scaled array (configs[3], one GPU's 256 of 2048 channels): 256 ant x 2048 beams x 256 ch, 32 chunks", "ms_per_launch": ms,
+            "samples_per_s": samples / (ms * 1e-3), "int8_tops": 8.0 * n_ant * n_beams * n_chan * cols / ms * 1e-9, "bound": "tensor"}, launches
+
+
 def run_ours(args):
     import torch
     import dsabeamformer_b200 as bf
@@ -339,6 +370,8 @@ def run_ours(args):
         dbg, dbg_launches = debug_shape_workload(bf, torch, local_rank, bf.compute_weights(pos, dirs, gpu=rank % 8))
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         dbg["frac_of_measured_hbm"] = dbg["hbm_gb_s_algorithmic"] / hbm_peak
+        big, big_launches = scaled_array_workload(bf, torch, local_rank)
+        big["frac_of_peak"] = big["int8_tops"] / peak
         line = {
             "metric": "beamformed samples/s (beams x chans x input-time)", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
@@ -360,7 +393,7 @@ def run_ours(args):
                              "sample": "4096 columns (2048 input times x 2 pol) x 256 channels, numpy complex128 matmul per channel, best of 5 passes of %.1f s" % cpu_s},
             "clocks": clocks,
             "reference_gpu_sm100": ref_gpu,
-            "other_workloads": [dbg],
+            "other_workloads": [dbg, big],
             "x_realtime_per_gpu": value / world / REALTIME_SAMPLES_PER_S,
             "int8_tops": value * OPS_PER_SAMPLE * 1e-12,
         }

@@ -20,10 +20,6 @@
 
 namespace {
 
-#ifdef DSABF_PROGRESS
-long long *g_progress = nullptr;    // zero-copy progress words of the streamed-weights kernel (debug builds only)
-#endif
-
 thread_local std::string g_last_error;
 
 int fail(int code, const char *what)
@@ -115,14 +111,6 @@ int run_fused(dsabf_handle *h, const uint8_t *d_packed, int n_chunks, float *d_o
     p.vdump = vdump;
     p.pdump = pdump;
     p.trace = h->d_trace;
-#ifdef DSABF_PROGRESS
-    if (getenv("DSABF_PROGRESS")) {
-        if (!g_progress) { CK(cudaHostAlloc(&g_progress, 2 * 4096 * sizeof(long long), cudaHostAllocMapped)); }
-        memset(g_progress, 0, 2 * 4096 * sizeof(long long));
-        g_progress[255 * 16] = (long long)h->launches;
-        p.trace = g_progress;
-    }
-#endif
     p.n_chan = h->cfg.n_channels;
     p.n_chunks = n_chunks;
     p.cols_per_chunk = h->cols_per_chunk;
@@ -466,23 +454,6 @@ int dsabf_debug_voltages_host(dsabf_handle *h, const void *packed, int n_chunks,
     if (e != cudaSuccess) return fail((int)e, "debug voltages");
     return 0;
 }
-
-#ifdef DSABF_PROGRESS
-void dsabf_debug_progress_dump(void)
-{
-    if (!g_progress) return;
-    fprintf(stderr, "progress (launch counter %lld): cta: role=code:count ...\n", g_progress[255 * 16]);
-    for (int b = 0; b < 148; b++) {
-        fprintf(stderr, "cta %3d:", b);
-        const long long t_start = g_progress[4096 + b * 16 + 15];
-        for (int r = 0; r < 11; r++)
-            if (g_progress[b * 16 + r])
-                fprintf(stderr, " %d=%lld:%u@%lldus", r, g_progress[b * 16 + r] >> 32, (unsigned)g_progress[b * 16 + r], (g_progress[4096 + b * 16 + r] - t_start) / 1000);
-        fprintf(stderr, " start=%lld", t_start);
-        fprintf(stderr, "\n");
-    }
-}
-#endif
 
 // debug: run one fused launch on device-resident data with the in-kernel clock trace on; trace_out: 2048 int64
 int dsabf_debug_trace(dsabf_handle *h, const void *d_packed, int n_chunks, float *d_out, long long *trace_out)

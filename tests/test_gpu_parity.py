@@ -248,6 +248,26 @@ def test_full_block_linearity_and_pol_time_invariance(bf, oracle):
     B.close()
 
 
+def test_scaled_array_full_shape_spot_rows(bf, oracle):
+    """BASELINE.json configs[3], one GPU's share: 256 antennas x 2048 beams x 256 channels (8 chunks = 2048
+    columns, 2048 work items over 148 CTAs, 128 weight tiles streamed per item).  (1) negating W leaves the
+    integer power unchanged bit for bit; (2) spot (chunk, channel) rows equal the oracle's int64 power."""
+    rng = np.random.default_rng(12)
+    w = rng.integers(-127, 128, size=(256, 256, 2048, 2), dtype=np.int8)
+    B = bf.Beamformer(debug=False, n_antennas=256, n_beams=2048, exact_power=1, power_scale=1.0)
+    B.set_weights(w)
+    packed = rng.integers(0, 256, size=(8, 256, 256, 256), dtype=np.uint8)
+    out = B.beamform(packed)
+    assert out.shape == (64, 256, 2048)
+    for c, f in ((0, 0), (3, 131), (7, 255)):
+        Vo = oracle.beamform(packed[c, f:f + 1], w[f:f + 1])
+        Po = oracle.power_int(Vo, 32)[:, 0]
+        assert np.array_equal(out[c * 8:(c + 1) * 8, f], Po.astype(np.float32)), (c, f)
+    B.set_weights((-w.astype(np.int16)).astype(np.int8))
+    assert np.array_equal(out, B.beamform(packed))
+    B.close()
+
+
 def test_full_debug_batch_dm0_against_oracle(bf, oracle, config_dir):
     """Config 1 end to end at full size: 1024 linear sources (256 MiB), DEBUG shape, DM-0 sums
     data.py-style [source][beam]; every 16th source checked against the oracle's float path."""

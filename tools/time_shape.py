@@ -37,10 +37,5 @@ def time_shape(n_ant, n_beams, n_chan, n_chunks, exact=0, reps=10, debug=False):
 
 if __name__ == "__main__":
     a = [int(v) for v in sys.argv[1:]]
-    try:
-        r = time_shape(a[0], a[1], a[2], a[3], a[4] if len(a) > 4 else 0, a[5] if len(a) > 5 else 10)
-    except Exception:
-        if hasattr(bf.lib(), "dsabf_debug_progress_dump"):
-            bf.lib().dsabf_debug_progress_dump()
-        raise
+    r = time_shape(a[0], a[1], a[2], a[3], a[4] if len(a) > 4 else 0, a[5] if len(a) > 5 else 10)
     print(json.dumps(r))
