@@ -201,6 +201,28 @@ def debug_shape_workload(bf, torch, device, weights):
     return {"workload": "DEBUG shape (N_AVERAGING=1): 4096 chunks of 262144 B, 256 ch x 256 beams (configs[1] shape)", "ms_per_launch": ms,
             "samples_per_s": samples / (ms * 1e-3), "hbm_gb_s_algorithmic": byts / ms * 1e-6, "bound": "hbm"}, launches
 
+def bind_near_gpu(torch, device):
+    """Pin this rank's host threads to the CPUs of the GPU's NUMA node (sysfs local_cpulist) before any pinned
+    buffer is allocated, so the staging memory is first-touched next to the GPU's PCIe root port -- the reference
+    binds its process the same way (`-c core`, beamformer.cu:111-116).  Returns a short description."""
+    try:
+        pr = torch.cuda.get_device_properties(device)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "unbound (no local cpulist)"
+        os.sched_setaffinity(0, cpus)
+        return "%d cpus local to %04x:%02x:%02x" % (len(cpus), pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except (OSError, AttributeError, ValueError) as e:
+        return "unbound (%s)" % type(e).__name__
+
+
 def scaled_array_workload(bf, torch, device):
     """BASELINE.json configs[3], one GPU's share of the frequency-sharded scaled array: 256 antennas x 2048 beams x
     256 channels, one 32-chunk block (8192 columns, 512 MiB in / 512 MiB out), device-resident, random int8 weights
@@ -242,6 +264,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         sys.exit("bench.py: no CUDA device (this framework has no CPU fallback; use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
+    host_binding = bind_near_gpu(torch, local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -383,7 +406,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": step_in_bytes, "d2h_bytes_per_step": step_out_bytes,
                     "ms_per_step": 1e3 * e2e_s_max / args.steps, "h2d_gb_s_per_gpu": step_in_bytes * args.steps / e2e_s_max * 1e-9,
                     "timing": "host clock between full device synchronisations (3 streams: H2D, compute, D2H)",
-                    "matches_device_path": same},
+                    "matches_device_path": same, "host_binding": host_binding},
             "gpu_launches": launches_total,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "fused_beamform_kernel<32,0>", "kernel_ms": kern_ms, "launches_timed": kern_n,

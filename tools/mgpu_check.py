@@ -57,8 +57,25 @@ full = torch.cat(gathered, dim=1).cpu().numpy()                              # [
 b0, b1 = D.beam_range(rank, world, 256)
 truth = O.dedisperse(np.ascontiguousarray(full[:, :, b0:b1]), delay, n_t_out)
 rel = np.abs(ded - truth) / np.maximum(np.abs(truth), 1e-30)
-ok &= bool(rel.max() <= 5e-6)
+# float32 sums of world*256 positive terms in two different orders (kernel: 4-channel chunks; oracle: sequential):
+# typical difference sqrt(n)*2^-24, allowed n*1e-8
+ok &= bool(rel.max() <= max(5e-6, 1e-8 * full.shape[1]))
 print("rank %d full-band dedispersion (all-to-all + kernel) vs oracle: max rel %.2e" % (rank, rel.max()), flush=True)
+
+# BASELINE.json configs[3] (scaled array, frequency-sharded): 256 antennas x 2048 beams, this rank's channels
+rng = np.random.default_rng(500 + rank)
+Bs = bf.Beamformer(debug=False, device=local, n_antennas=256, n_beams=2048, n_channels=3)
+ws = rng.integers(-127, 128, size=(3, 256, 2048, 2), dtype=np.int8)
+Bs.set_weights(ws)
+xs = rng.integers(0, 256, size=(2, 3, Bs.cols_per_chunk, 256), dtype=np.uint8)
+ps = Bs.beamform(xs)
+worst = 0.0
+for c in range(2):
+    ref = O.detect_ref_float(O.beamform(xs[c], ws), 32)
+    worst = max(worst, float((np.abs(ps[c * 8:(c + 1) * 8] - ref) / np.maximum(ref, 1e-30)).max()))
+ok &= bool(worst <= 1e-6)
+print("rank %d scaled-array shard (256 ant x 2048 beams) vs oracle: max rel %.2e" % (rank, worst), flush=True)
+Bs.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 B.close()
