@@ -459,6 +459,9 @@ int dsabf_debug_voltages_host(dsabf_handle *h, const void *packed, int n_chunks,
 int dsabf_debug_trace(dsabf_handle *h, const void *d_packed, int n_chunks, float *d_out, long long *trace_out)
 {
     if (!h || !d_packed || !d_out || !trace_out) return fail(DSABF_E_INVALID, "bad argument");
+#ifndef DSABF_TRACE
+    return fail(DSABF_E_STATE, "library built without -DDSABF_TRACE (make EXTRA=-DDSABF_TRACE)");
+#else
     CK(cudaSetDevice(h->device));
     CK(cudaMalloc(&h->d_trace, 2048 * sizeof(long long)));
     CK(cudaMemset(h->d_trace, 0, 2048 * sizeof(long long)));
@@ -470,6 +473,7 @@ int dsabf_debug_trace(dsabf_handle *h, const void *d_packed, int n_chunks, float
     if (rc) return rc;
     if (e != cudaSuccess) return fail((int)e, "trace");
     return 0;
+#endif
 }
 
 // ---- dedispersion -------------------------------------------------------------

@@ -38,6 +38,14 @@ using namespace fused;
 
 namespace {
 
+// In-kernel clock64 trace (dsabf_debug_trace, tools/trace_one.py): compiled in only with -DDSABF_TRACE; the
+// predicated stamps cost ~15 of the epilogue's 165 instructions per accumulator stage even when switched off.
+#ifdef DSABF_TRACE
+constexpr bool kTrace = true;
+#else
+constexpr bool kTrace = false;
+#endif
+
 
 struct __align__(1024) Smem {
     uint8_t a[kMaxMT][kATileBytes];      // 64 KB  resident weights of the current channel
@@ -164,17 +172,17 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                         touched = true;
                     }
                     if (!((seen >> m) & 1u)) { mbar_wait(bar_a_full + 8 * m, ch & 1, 4); seen |= 1u << m; }
-                    const long long tr0 = p.trace ? clock64() : 0;
+                    const long long tr0 = (kTrace && p.trace) ? clock64() : 0;
                     mbar_wait(bar_acc_empty + 8 * me, (use & 1) ^ 1, 5);
                     tc_fence_after();
-                    if (p.trace && blockIdx.x == 0 && acc_cnt < 128) { p.trace[acc_cnt * 16 + 0] = tr0; p.trace[acc_cnt * 16 + 1] = clock64(); }
+                    if (kTrace && p.trace && blockIdx.x == 0 && acc_cnt < 128) { p.trace[acc_cnt * 16 + 0] = tr0; p.trace[acc_cnt * 16 + 1] = clock64(); }
                     const uint64_t adesc = make_desc_k_sw128(a_smem + m * kATileBytes);
                     const uint32_t d = tmem_base + me * kAccCols;
 #pragma unroll
                     for (int k = 0; k < kRowBytes / 32; k++)   // K = 32 bytes per instruction; +32 B = +2 in the descriptor
                         mma_i8_ss(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0);
                     tc_commit(bar_acc_full + 8 * me);
-                    if (p.trace && blockIdx.x == 0 && acc_cnt < 128) p.trace[acc_cnt * 16 + 2] = clock64();
+                    if (kTrace && p.trace && blockIdx.x == 0 && acc_cnt < 128) p.trace[acc_cnt * 16 + 2] = clock64();
                     if (last_of_ch) { tc_commit(bar_a_empty + 8 * m); released |= 1u << m; }
                     use++;
                 }
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
         const uint32_t st_im = r * 128 + (((c + 4) ^ r) << 4);
         for (int item = item_begin, it = 0; item < item_end; item++, it++) {
             const int s = it % kStages, buf = it & 1;
-            const bool utr = p.trace && blockIdx.x == 0 && uw == 0 && lane == 0 && it < 32;
+            const bool utr = kTrace && p.trace && blockIdx.x == 0 && uw == 0 && lane == 0 && it < 32;
             if (utr) p.trace[it * 64 + 12] = clock64();
             mbar_wait<200>(bar_stg_full + 8 * s, (it / kStages) & 1, 6);
             if (utr) p.trace[it * 64 + 13] = clock64();
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
 #pragma unroll 1
             for (int m = 0; m < mt; m++, acc_cnt++) {
                 const uint32_t as = acc_cnt & 1;
-                const bool trc = p.trace && blockIdx.x == 0 && (ew == 0 || ew == 15) && lane == 0 && acc_cnt < 128;
+                const bool trc = kTrace && p.trace && blockIdx.x == 0 && (ew == 0 || ew == 15) && lane == 0 && acc_cnt < 128;
                 const int trb = acc_cnt * 16 + (ew == 0 ? 4 : 8);
                 if (trc) p.trace[trb + 0] = clock64();
                 mbar_wait(bar_acc_full + 8 * as, (acc_cnt >> 1) & 1, 8);
