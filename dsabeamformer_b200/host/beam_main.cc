@@ -56,6 +56,11 @@ int main(int argc, char *argv[])
     dsabf_config cfg;
     CHK(dsabf_default_config(&cfg, debug));
     if (const char *dev = getenv("DSABF_DEVICE")) cfg.device = atoi(dev);   // CUDA ordinal; -g stays the sub-band index
+    // The reference fixes the array shape at compile time (beamformer.hh:47-53); here it is run-time.  These
+    // overrides select e.g. the scaled array (256 antennas x 2048 beams) without a rebuild.
+    if (const char *v = getenv("DSABF_N_ANTENNAS")) cfg.n_antennas = atoi(v);
+    if (const char *v = getenv("DSABF_N_BEAMS")) cfg.n_beams = atoi(v);
+    if (const char *v = getenv("DSABF_N_CHANNELS")) cfg.n_channels = atoi(v);
 
     std::vector<Antenna> pos(cfg.n_antennas);
     std::vector<Direction> dir(cfg.n_beams);

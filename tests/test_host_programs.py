@@ -101,6 +101,27 @@ def test_debug_program_matches_oracle_and_reference_binary(oracle, config_dir, t
 
 
 @pytest.mark.gpu
+def test_debug_program_scaled_array(oracle, config_dir, tmp_path):
+    """BASELINE.json configs[3] through the drop-in program: 256 antennas x 2048 beams (16 channels of the band),
+    64 seeded sources; bin/data.py [source][beam] against the oracle's float path."""
+    cfg = [os.path.join(config_dir, f) for f in ("scaled_positions_256.txt", "scaled_beam_directions_2048.txt", "scaled_source_directions_64.txt")]
+    work = tmp_path / "scaled"; (work / "bin").mkdir(parents=True)
+    env = dict(os.environ, DSABF_N_ANTENNAS="256", DSABF_N_BEAMS="2048", DSABF_N_CHANNELS="16")
+    r = subprocess.run([_need("beam_debug"), "-g", "3", "-p", cfg[0], "-d", cfg[1], "-s", cfg[2]], cwd=work, capture_output=True, text=True,
+                       timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ours = _load_data_py(work / "bin" / "data.py")
+    assert ours.shape == (64, 2048)
+    pos = oracle.read_positions(cfg[0], 256); dirs = oracle.read_directions(cfg[1], 2048); src = oracle.read_directions(cfg[2])
+    w = oracle.weights(pos, dirs, 3, n_chan=16)
+    data = oracle.generate(pos, src, n_chunks=64, n_chan=16, gpu=3)
+    for s in (0, 1, 31, 63):
+        ref = oracle.dm0(oracle.detect_ref_float(oracle.beamform(data[s], w), 2))
+        assert np.allclose(ours[s], ref, rtol=2e-5), s
+        assert ref.max() > 50 * np.median(ref)                  # a point source lights up a beam
+
+
+@pytest.mark.gpu
 def test_observation_program_streams_from_ring(config_dir):
     """Config 3: bin/beam reads 134217728-byte blocks from the ring (25-block burn-in, then data),
     copies them through pinned memory into the device ring, beamforms, and ends at the short block."""

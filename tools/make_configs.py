@@ -70,6 +70,18 @@ def grid_dirs(n):
     return [(_g(a), _g(b)) for a, b in zip(t.ravel(), p.ravel())]
 
 
+def scaled_dirs(n_theta=64, n_phi=32):
+    """BASELINE.json configs[3]: 2048 beam directions, 64 x 32 grid over the same +-3.5 degree field."""
+    t, p = np.meshgrid(np.linspace(-HALF_FOV, HALF_FOV, n_theta), np.linspace(-HALF_FOV, HALF_FOV, n_phi))
+    return [(_g(a), _g(b)) for a, b in zip(t.ravel(), p.ravel())]
+
+
+def scaled_sources(n=64, seed=0xD5A):
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(-HALF_FOV, HALF_FOV, size=(n, 2))
+    return [(_g(a), _g(b)) for a, b in ang]
+
+
 DADA_HEADER = [
     ("HDR_VERSION", "1.0"), ("HDR_SIZE", "4096"), ("INSTRUMENT", "DSAX"), ("TELESCOPE", "DSA-10"),
     ("SOURCE", "TEST"), ("MODE", "RAW"), ("NBIT", "4"), ("NDIM", "1"), ("NPOL", "2"), ("NCHAN", "2048"),
@@ -93,6 +105,10 @@ def make_all(outdir):
     _write(j("linear_source_directions_1024.txt"), 1024, linear_dirs(1024, "0.0"), "\t")
     _write(j("grid_source_directions_3721.txt"), 3721, grid_dirs(3721), "\t")
     _write(j("grid_source_directions_4096.txt"), 4096, grid_dirs(4096), "\t")
+    # scaled array (BASELINE.json configs[3]): 16 x 16 antennas over +-250 m, 2048 beams, 64 seeded random sources
+    _write(j("scaled_positions_256.txt"), 256, grid_positions(256), " ")
+    _write(j("scaled_beam_directions_2048.txt"), 2048, scaled_dirs(), "\t")
+    _write(j("scaled_source_directions_64.txt"), 64, scaled_sources(), "\t")
     with open(j("correlator_header_dsaX.txt"), "w") as f:
         for k, v in DADA_HEADER:
             f.write("%-12s %s\n" % (k, v))
