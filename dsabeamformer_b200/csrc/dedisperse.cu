@@ -16,7 +16,8 @@
 // conflict-free).  Each staged value is used by up to 8 trials, so global traffic per add is
 // ~1/16 of a float; every add costs one 4-byte shared-memory read per lane, which is the
 // structural bound of brute-force dedispersion (32 adds/clk/SM).  With few trials the kernel is
-// HBM-bound (power read once), with many it is shared-memory-bound.
+// HBM-bound (power read once), with many it is shared-memory-bound.  Fewer than 8 trials: the warps
+// split the 32 output times (TSPLIT); a grid under two waves runs a 4-deep cp.async pipeline (STAGES).
 #include "fused_beamform.cuh"
 
 namespace dsabf {
@@ -42,31 +43,43 @@ struct ChunkMeta {
     int off[DD_FC][DD_DMS];      // delay - dmin per trial
 };
 
+template <int STAGES, int TSPLIT>
 __global__ void __launch_bounds__(DD_THREADS)
 dedisperse_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_beams, const int32_t *__restrict__ delay, int n_dm,
                   int n_t_out, float *__restrict__ out)
 {
     extern __shared__ __align__(16) uint8_t dd_smem[];
-    float (*win)[DD_FC][DD_WIN][DD_BB] = reinterpret_cast<float (*)[DD_FC][DD_WIN][DD_BB]>(dd_smem);          // [2]
-    ChunkMeta *meta = reinterpret_cast<ChunkMeta *>(dd_smem + sizeof(float) * 2 * DD_FC * DD_WIN * DD_BB);  // [2]
+    float (*win)[DD_FC][DD_WIN][DD_BB] = reinterpret_cast<float (*)[DD_FC][DD_WIN][DD_BB]>(dd_smem);               // [STAGES]
+    ChunkMeta *meta = reinterpret_cast<ChunkMeta *>(dd_smem + sizeof(float) * STAGES * DD_FC * DD_WIN * DD_BB);  // [STAGES]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b0 = blockIdx.x * DD_BB, t0 = blockIdx.y * DD_TT, d0 = blockIdx.z * DD_DMS;
-    const int nd = min(DD_DMS, n_dm - d0);
-    const bool my_dm = warp < nd;
+    // DM slab fastest: the CTAs that read the same (time, beam) window of the power run together and share it in L2
+    const int d0 = blockIdx.x * (DD_DMS / TSPLIT), t0 = blockIdx.y * DD_TT, b0 = blockIdx.z * DD_BB;
+    const int nd = min(DD_DMS / TSPLIT, n_dm - d0);
+    // With fewer than 8 trials per CTA the warps split the 32 output times instead (TSPLIT slices of TW times)
+    constexpr int TW = DD_TT / TSPLIT;
+    const int dw = warp % (DD_DMS / TSPLIT), tofs = (warp / (DD_DMS / TSPLIT)) * TW;
+    const bool my_dm = dw < nd;
     const bool my_beam = (b0 + lane) < n_beams;
     const int n_chunks = (n_chan + DD_FC - 1) / DD_FC;
 
-    float acc[DD_TT];
+    float acc[TW];
 #pragma unroll
-    for (int t = 0; t < DD_TT; t++) acc[t] = 0.f;
+    for (int t = 0; t < TW; t++) acc[t] = 0.f;
 
+    // delay of (channel fi of chunk c, trial w) for the 32 metadata threads; fetched one iteration ahead of its
+    // use so that the global-load latency is off the per-chunk critical path
+    auto load_delay = [&](int c) -> int {
+        if (threadIdx.x >= DD_FC * DD_DMS) return 0;
+        const int fi = threadIdx.x / DD_DMS, w = threadIdx.x % DD_DMS;
+        const int f = c * DD_FC + fi;
+        return (w < nd && f < n_chan) ? delay[(size_t)(d0 + w) * n_chan + f] : 0x3fffffff;
+    };
     // stage chunk c into buffer buf: metadata by the first 32 threads, rows by everybody (cp.async, 16 B)
-    auto stage = [&](int c, int buf) {
+    auto stage = [&](int c, int buf, int dl) {
         if (threadIdx.x < DD_FC * DD_DMS) {
             const int fi = threadIdx.x / DD_DMS, w = threadIdx.x % DD_DMS;
             const int f = c * DD_FC + fi;
-            int dl = (w < nd && f < n_chan) ? delay[(size_t)(d0 + w) * n_chan + f] : 0x3fffffff;
             int mn = dl, mx = (w < nd && f < n_chan) ? dl : 0;
 #pragma unroll
             for (int o = DD_DMS / 2; o > 0; o >>= 1) {     // the 8 trials of one channel sit in 8 consecutive lanes
@@ -102,10 +115,18 @@ dedisperse_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_be
         cp_async_commit();
     };
 
-    stage(0, 0);
+    // STAGES-deep cp.async pipeline: chunks c+1 .. c+STAGES-1 are in flight while chunk c is summed.  One commit
+    // group per iteration (empty past the end) keeps the group arithmetic uniform.
+    for (int c = 0; c < STAGES - 1; c++) {
+        if (c < n_chunks) stage(c, c, load_delay(c)); else cp_async_commit();
+    }
+    int dl_next = load_delay(STAGES - 1);
     for (int c = 0; c < n_chunks; c++) {
-        const int buf = c & 1;
-        if (c + 1 < n_chunks) { stage(c + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        const int buf = c % STAGES;
+        const int dl_now = dl_next;
+        dl_next = load_delay(c + STAGES);
+        if (c + STAGES - 1 < n_chunks) stage(c + STAGES - 1, (c + STAGES - 1) % STAGES, dl_now); else cp_async_commit();
+        cp_async_wait<STAGES - 1>();
         __syncthreads();                                   // chunk c (and its metadata) visible to all warps
         if (my_dm) {
 #pragma unroll
@@ -113,17 +134,17 @@ dedisperse_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_be
                 const int f = c * DD_FC + fi;
                 if (f >= n_chan) break;
                 const int rows = meta[buf].rows[fi];
-                const int off = meta[buf].off[fi][warp];
+                const int off = meta[buf].off[fi][dw];
                 if (rows > 0) {
-                    const float *w0 = &win[buf][fi][off][lane];
+                    const float *w0 = &win[buf][fi][off + tofs][lane];
 #pragma unroll
-                    for (int t = 0; t < DD_TT; t++) acc[t] += w0[t * DD_BB];
+                    for (int t = 0; t < TW; t++) acc[t] += w0[t * DD_BB];
                 } else if (my_beam) {
                     // this group's delays are too spread out at this channel: read the rows directly
                     const int dl = meta[buf].dmin[fi] + off;
 #pragma unroll
-                    for (int t = 0; t < DD_TT; t++) {
-                        const int tt = t0 + t + dl;
+                    for (int t = 0; t < TW; t++) {
+                        const int tt = t0 + tofs + t + dl;
                         if (tt < n_t) acc[t] += power[((size_t)tt * n_chan + f) * n_beams + b0 + lane];
                     }
                 }
@@ -133,11 +154,26 @@ dedisperse_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_be
     }
 
     if (my_dm && my_beam) {
-        float *o = out + ((size_t)(d0 + warp) * n_t_out + t0) * n_beams + b0 + lane;
+        float *o = out + ((size_t)(d0 + dw) * n_t_out + t0 + tofs) * n_beams + b0 + lane;
 #pragma unroll
-        for (int t = 0; t < DD_TT; t++)
-            if (t0 + t < n_t_out) o[(size_t)t * n_beams] = acc[t];
+        for (int t = 0; t < TW; t++)
+            if (t0 + tofs + t < n_t_out) o[(size_t)t * n_beams] = acc[t];
     }
+}
+
+template <int STAGES, int TSPLIT>
+cudaError_t launch_stages(dim3 grid, const float *d_power, int n_t, int n_chan, int n_beams, const int32_t *d_delay, int n_dm, int n_t_out,
+                          float *d_out, cudaStream_t stream)
+{
+    constexpr size_t smem = sizeof(float) * STAGES * DD_FC * DD_WIN * DD_BB + STAGES * sizeof(ChunkMeta);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(dedisperse_kernel<STAGES, TSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dedisperse_kernel<STAGES, TSPLIT><<<grid, DD_THREADS, smem, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_dm, n_t_out, d_out);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -146,17 +182,30 @@ cudaError_t launch_dedisperse(const float *d_power, int n_t, int n_chan, int n_b
                               float *d_out, cudaStream_t stream)
 {
     if (n_dm <= 0 || n_t_out <= 0) return cudaSuccess;
-    dim3 grid((n_beams + DD_BB - 1) / DD_BB, (n_t_out + DD_TT - 1) / DD_TT, (n_dm + DD_DMS - 1) / DD_DMS);
+    // fewer than 8 trials: the 8 warps of a CTA split the output times instead of idling (tsplit = 8, 4, 2 for 1, 2, <=4 trials)
+    const int tsplit = n_dm >= 5 ? 1 : (n_dm >= 3 ? 2 : (n_dm == 2 ? 4 : 8));
+    const int dms_per_cta = DD_DMS / tsplit;
+    dim3 grid((n_dm + dms_per_cta - 1) / dms_per_cta, (n_t_out + DD_TT - 1) / DD_TT, (n_beams + DD_BB - 1) / DD_BB);
     if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidValue;
-    constexpr size_t smem = sizeof(float) * 2 * DD_FC * DD_WIN * DD_BB + 2 * sizeof(ChunkMeta);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dedisperse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // Few CTAs (few DM trials): each walks all channels serially and the kernel is bound by load latency, so
+    // keep 3 chunks (48 KB) in flight per CTA; many CTAs: 2 stages and 3 CTAs per SM hide it better.
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
-    dedisperse_kernel<<<grid, DD_THREADS, smem, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_dm, n_t_out, d_out);
-    return cudaGetLastError();
+    const long long n_cta = (long long)grid.x * grid.y * grid.z;
+    const bool deep = n_cta <= 2LL * num_sms;
+#define DD_LAUNCH(S, T) launch_stages<S, T>(grid, d_power, n_t, n_chan, n_beams, d_delay, n_dm, n_t_out, d_out, stream)
+    switch (tsplit) {
+    case 1: return deep ? DD_LAUNCH(4, 1) : DD_LAUNCH(2, 1);
+    case 2: return deep ? DD_LAUNCH(4, 2) : DD_LAUNCH(2, 2);
+    case 4: return deep ? DD_LAUNCH(4, 4) : DD_LAUNCH(2, 4);
+    default: return deep ? DD_LAUNCH(4, 8) : DD_LAUNCH(2, 8);
+    }
+#undef DD_LAUNCH
 }
 
 }  // namespace dsabf

@@ -277,10 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 if (trc) p.trace[trb + 1] = clock64();
                 const uint32_t taddr = tbase_w + as * kAccCols;
                 uint32_t va[32], vb[32];
-                tmem_ld_32x32(taddr, va);
-                tmem_ld_32x32(taddr + 32, vb);
-                tmem_ld_wait(va);
-                tmem_ld_wait(vb);
+                tmem_ld_2x32_wait(taddr, va, vb);
                 // both halves are in registers: hand the TMEM stage back to the MMA right away
                 tc_fence_before();
                 __syncwarp();

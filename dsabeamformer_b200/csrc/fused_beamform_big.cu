@@ -230,10 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
                 tc_fence_after();
                 const uint32_t taddr = tbase_w + as * kAccCols;
                 uint32_t va[32], vb[32];
-                tmem_ld_32x32(taddr, va);
-                tmem_ld_32x32(taddr + 32, vb);
-                tmem_ld_wait(va);
-                tmem_ld_wait(vb);
+                tmem_ld_2x32_wait(taddr, va, vb);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);

@@ -206,6 +206,23 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32])
                  : "memory");
 }
 
+// Two adjacent 32-column loads and the wait in ONE asm statement: one TMEM address operand (one R2UR instead
+// of two), and the consumers of a[]/b[] cannot be scheduled above the wait because the registers are
+// outputs of the statement that contains it.
+__device__ __forceinline__ void tmem_ld_2x32_wait(uint32_t taddr, uint32_t (&a)[32], uint32_t (&b)[32])
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 t1;\n\t"
+        "add.u32 t1, %64, 32;\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [t1];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n\t"
+        "}"
+        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31]), "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]), "=r"(b[16]), "=r"(b[17]), "=r"(b[18]), "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]), "=r"(b[24]), "=r"(b[25]), "=r"(b[26]), "=r"(b[27]), "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
+        : "r"(taddr)
+        : "memory");
+}
 
 // ---- the same operations on precomputed 32-bit shared-memory addresses (hot loops:
 // the generic->shared conversion is otherwise redone at every use) ----

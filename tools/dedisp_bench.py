@@ -23,19 +23,21 @@ with torch.cuda.stream(st):
     out = torch.empty((n_dm, n_t_out, n_beams), dtype=torch.float32, device="cuda")
     for _ in range(2):
         B.dedisperse_device(power.data_ptr(), n_t, n_chan, n_beams, delay, n_t_out, out.data_ptr(), st.cuda_stream)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    e0.record(st)
-    for _ in range(reps):
-        B.dedisperse_device(power.data_ptr(), n_t, n_chan, n_beams, delay, n_t_out, out.data_ptr(), st.cuda_stream)
-    e1.record(st)
-    torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / reps
+    reps, batches = 10, []
+    for _ in range(5):                      # 5 batches of 10 launches: report the median batch (run-to-run spread is large)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps):
+            B.dedisperse_device(power.data_ptr(), n_t, n_chan, n_beams, delay, n_t_out, out.data_ptr(), st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize()
+        batches.append(e0.elapsed_time(e1) / reps)
+ms = sorted(batches)[len(batches) // 2]
 algo = 4.0 * n_t * n_chan * n_beams + 4.0 * n_dm * n_t_out * n_beams
 adds = float(n_dm) * n_chan * n_beams * n_t_out
 # spot check vs oracle on a slice of beams / trials
 sub = O.dedisperse(power[:, :, :2].cpu().numpy(), delay[:3], n_t_out)
 got = out[:3, :, :2].cpu().numpy()
 print(json.dumps({"kernel": "dedisperse_kernel", "n_t": n_t, "n_chan": n_chan, "n_beams": n_beams, "n_dm": n_dm, "n_t_out": n_t_out,
-                  "max_delay": int(delay.max()), "ms": ms, "algorithmic_GB_s": algo / ms * 1e-6, "Gadds_s": adds / ms * 1e-6,
+                  "max_delay": int(delay.max()), "ms": ms, "ms_batches": [round(b, 4) for b in batches], "algorithmic_GB_s": algo / ms * 1e-6, "Gadds_s": adds / ms * 1e-6,
                   "max_rel_vs_oracle": float((np.abs(got - sub) / np.maximum(np.abs(sub), 1e-30)).max())}))
