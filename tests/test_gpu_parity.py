@@ -299,11 +299,14 @@ def test_full_debug_batch_dm0_against_oracle(bf, oracle, config_dir):
     B.close()
 
 
-def test_dedisperse_matches_oracle(bf, oracle):
+@pytest.mark.parametrize("n_dm,n_chan,n_beams", [(13, 64, 128), (1, 64, 128), (2, 37, 40), (3, 64, 32), (4, 10, 96), (5, 64, 34), (8, 3, 64)])
+def test_dedisperse_matches_oracle(bf, oracle, n_dm, n_chan, n_beams):
+    """every warps-per-trial split of the kernel (1, 2, 3-4, 5+ trials), ragged channel chunks and beam tiles,
+    a time tile that is cut by n_t_out"""
     rng = np.random.default_rng(9)
-    n_t, n_chan, n_beams = 96, 64, 128
+    n_t = 96
     power = rng.random((n_t, n_chan, n_beams), dtype=np.float32) * 100
-    dms = oracle.dm_trials(300.0, 2048)[::4][:13]
+    dms = oracle.dm_trials(300.0, 2048)[::4][:n_dm]
     freq = 1.53 - np.arange(n_chan) * (0.25 / n_chan)
     delay = oracle.dm_delays(dms, freq)
     delay = np.minimum(delay, 60)
