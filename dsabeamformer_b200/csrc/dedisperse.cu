@@ -18,6 +18,7 @@
 // structural bound of brute-force dedispersion (32 adds/clk/SM).  With few trials the kernel is
 // HBM-bound (power read once), with many it is shared-memory-bound.  Fewer than 8 trials: the warps
 // split the 32 output times (TSPLIT); a grid under two waves runs a 4-deep cp.async pipeline (STAGES).
+#include <cstdint>
 #include "fused_beamform.cuh"
 
 namespace dsabf {
@@ -161,6 +162,59 @@ dedisperse_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_be
     }
 }
 
+// One trial (DM 0 = the reference's DEBUG cublasSgemv, beamformer.cu:498-504, or any single delay curve): nothing is
+// shared between trials, so skip shared memory.  Thread = (output time, 4 beams): 16-byte loads, coalesced across the
+// warp (512 contiguous bytes), 8 channels in flight per thread, channels added in order.  Pure streaming: HBM-bound.
+constexpr int DS_UNROLL = 8;
+// SPLIT > 1: small problems do not fill the machine with one thread per (time, 4 beams); SPLIT threads then share the
+// channel range of an item and slice 0 adds the partial sums in slice order (deterministic).
+template <int SPLIT>
+__global__ void __launch_bounds__(256)
+dedisperse_single_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_beams, const int32_t *__restrict__ delay, int n_t_out,
+                         float *__restrict__ out)
+{
+    constexpr int ITEMS = 256 / SPLIT;
+    __shared__ float4 red[SPLIT > 1 ? SPLIT - 1 : 1][ITEMS];
+    const int b4 = n_beams >> 2;                                      // float4 per row
+    const int li = threadIdx.x % ITEMS, slice = threadIdx.x / ITEMS;
+    const long long idx = (long long)blockIdx.x * ITEMS + li;
+    const bool live = idx < (long long)n_t_out * b4;
+    const int t = live ? (int)(idx / b4) : 0, q = live ? (int)(idx - (long long)t * b4) : 0;
+    const float4 *src = reinterpret_cast<const float4 *>(power) + q;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int per = (n_chan + SPLIT - 1) / SPLIT;
+    int f = slice * per;
+    const int f_end = min(n_chan, f + per);
+    if (live) {
+        for (; f + DS_UNROLL <= f_end; f += DS_UNROLL) {
+            float4 v[DS_UNROLL];
+#pragma unroll
+            for (int u = 0; u < DS_UNROLL; u++) {
+                const int tt = t + __ldg(delay + f + u);
+                v[u] = (tt < n_t) ? __ldcs(src + ((size_t)tt * n_chan + f + u) * b4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < DS_UNROLL; u++) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        for (; f < f_end; f++) {
+            const int tt = t + __ldg(delay + f);
+            if (tt < n_t) {
+                const float4 v = __ldcs(src + ((size_t)tt * n_chan + f) * b4);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+    }
+    if (SPLIT > 1) {
+        if (slice > 0) red[slice - 1][li] = acc;
+        __syncthreads();
+        if (slice == 0) {
+#pragma unroll
+            for (int s2 = 0; s2 < SPLIT - 1; s2++) { const float4 r = red[s2][li]; acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w; }
+        }
+    }
+    if (live && slice == 0) reinterpret_cast<float4 *>(out)[(size_t)t * b4 + q] = acc;
+}
+
 template <int STAGES, int TSPLIT>
 cudaError_t launch_stages(dim3 grid, const float *d_power, int n_t, int n_chan, int n_beams, const int32_t *d_delay, int n_dm, int n_t_out,
                           float *d_out, cudaStream_t stream)
@@ -182,6 +236,14 @@ cudaError_t launch_dedisperse(const float *d_power, int n_t, int n_chan, int n_b
                               float *d_out, cudaStream_t stream)
 {
     if (n_dm <= 0 || n_t_out <= 0) return cudaSuccess;
+    if (n_dm == 1 && (n_beams & 3) == 0 && ((uintptr_t)d_power & 15) == 0 && ((uintptr_t)d_out & 15) == 0) {
+        const long long n = (long long)n_t_out * (n_beams >> 2);
+        // fewer than ~4 resident warps' worth of items per SM: split the channel range over 4 or 8 threads
+        if (n >= 65536) dedisperse_single_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
+        else if (n >= 16384) dedisperse_single_kernel<4><<<(unsigned)((n + 63) / 64), 256, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
+        else dedisperse_single_kernel<8><<<(unsigned)((n + 31) / 32), 256, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
+        return cudaGetLastError();
+    }
     // fewer than 8 trials: the 8 warps of a CTA split the output times instead of idling (tsplit = 8, 4, 2 for 1, 2, <=4 trials)
     const int tsplit = n_dm >= 5 ? 1 : (n_dm >= 3 ? 2 : (n_dm == 2 ? 4 : 8));
     const int dms_per_cta = DD_DMS / tsplit;

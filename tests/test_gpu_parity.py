@@ -299,7 +299,7 @@ def test_full_debug_batch_dm0_against_oracle(bf, oracle, config_dir):
     B.close()
 
 
-@pytest.mark.parametrize("n_dm,n_chan,n_beams", [(13, 64, 128), (1, 64, 128), (2, 37, 40), (3, 64, 32), (4, 10, 96), (5, 64, 34), (8, 3, 64)])
+@pytest.mark.parametrize("n_dm,n_chan,n_beams", [(13, 64, 128), (1, 64, 128), (1, 21, 34), (2, 37, 40), (3, 64, 32), (4, 10, 96), (5, 64, 34), (8, 3, 64)])
 def test_dedisperse_matches_oracle(bf, oracle, n_dm, n_chan, n_beams):
     """every warps-per-trial split of the kernel (1, 2, 3-4, 5+ trials), ragged channel chunks and beam tiles,
     a time tile that is cut by n_t_out"""
