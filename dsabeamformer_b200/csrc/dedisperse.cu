@@ -67,6 +67,13 @@ dedisperse_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_be
     float acc[TW];
 #pragma unroll
     for (int t = 0; t < TW; t++) acc[t] = 0.f;
+    // TSPLIT == 1 (8 trials per CTA): a warp owns a PAIR of adjacent trials and half of the output times.  Adjacent
+    // trials' delays at one channel differ by 0 or 1 sample almost always (725 samples spread over 1627 trials at the
+    // bottom of the band), so the pair shares its shared-memory reads: 16 or 17 loads feed 32 adds instead of 32.
+    // acc[] then holds trial A in [0, PT) and trial B in [PT, 2 PT).
+    constexpr int PT = DD_TT / 2;
+    const int pr = warp & 3, th = warp >> 2;
+    const bool has_a = 2 * pr < nd, has_b = 2 * pr + 1 < nd;
 
     // delay of (channel fi of chunk c, trial w) for the 32 metadata threads; fetched one iteration ahead of its
     // use so that the global-load latency is off the per-chunk critical path
@@ -129,7 +136,45 @@ dedisperse_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_be
         if (c + STAGES - 1 < n_chunks) stage(c + STAGES - 1, (c + STAGES - 1) % STAGES, dl_now); else cp_async_commit();
         cp_async_wait<STAGES - 1>();
         __syncthreads();                                   // chunk c (and its metadata) visible to all warps
-        if (my_dm) {
+        if (TSPLIT == 1) {
+            if (has_a) {
+#pragma unroll
+                for (int fi = 0; fi < DD_FC; fi++) {
+                    const int f = c * DD_FC + fi;
+                    if (f >= n_chan) break;
+                    const int rows = meta[buf].rows[fi];
+                    const int offa = meta[buf].off[fi][2 * pr];
+                    const int offb = has_b ? meta[buf].off[fi][2 * pr + 1] : offa;
+                    if (rows > 0) {
+                        const float *wa = &win[buf][fi][offa + th * PT][lane];
+                        const int delta = offb - offa;
+                        if (delta == 0) {
+#pragma unroll
+                            for (int t = 0; t < PT; t++) { const float v = wa[t * DD_BB]; acc[t] += v; acc[PT + t] += v; }
+                        } else if (delta == 1) {
+                            float v[PT + 1];
+#pragma unroll
+                            for (int t = 0; t <= PT; t++) v[t] = wa[t * DD_BB];
+#pragma unroll
+                            for (int t = 0; t < PT; t++) { acc[t] += v[t]; acc[PT + t] += v[t + 1]; }
+                        } else {
+                            const float *wb = &win[buf][fi][offb + th * PT][lane];
+#pragma unroll
+                            for (int t = 0; t < PT; t++) { acc[t] += wa[t * DD_BB]; acc[PT + t] += wb[t * DD_BB]; }
+                        }
+                    } else if (my_beam) {
+                        // this group's delays are too spread out at this channel: read the rows directly
+                        const int dla = meta[buf].dmin[fi] + offa, dlb = meta[buf].dmin[fi] + offb;
+#pragma unroll
+                        for (int t = 0; t < PT; t++) {
+                            const int ta = t0 + th * PT + t + dla, tb = t0 + th * PT + t + dlb;
+                            if (ta < n_t) acc[t] += power[((size_t)ta * n_chan + f) * n_beams + b0 + lane];
+                            if (tb < n_t) acc[PT + t] += power[((size_t)tb * n_chan + f) * n_beams + b0 + lane];
+                        }
+                    }
+                }
+            }
+        } else if (my_dm) {
 #pragma unroll
             for (int fi = 0; fi < DD_FC; fi++) {
                 const int f = c * DD_FC + fi;
@@ -154,7 +199,19 @@ dedisperse_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_be
         __syncthreads();                                   // everybody done with buf before it is re-staged
     }
 
-    if (my_dm && my_beam) {
+    if (TSPLIT == 1) {
+        if (my_beam) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (h == 0 ? has_a : has_b) {
+                    float *o = out + ((size_t)(d0 + 2 * pr + h) * n_t_out + t0 + th * PT) * n_beams + b0 + lane;
+#pragma unroll
+                    for (int t = 0; t < PT; t++)
+                        if (t0 + th * PT + t < n_t_out) o[(size_t)t * n_beams] = acc[h * PT + t];
+                }
+            }
+        }
+    } else if (my_dm && my_beam) {
         float *o = out + ((size_t)(d0 + dw) * n_t_out + t0 + tofs) * n_beams + b0 + lane;
 #pragma unroll
         for (int t = 0; t < TW; t++)
