@@ -65,6 +65,25 @@ def dedisperse_full_band(beamformer, power_local, delay_full, n_t_out, group=Non
     T, C, Bs = full.shape
     n_dm = delay_full.shape[0]
     out = torch.empty((n_dm, n_t_out, Bs), dtype=torch.float32, device=full.device)
-    beamformer.dedisperse_device(full.data_ptr(), T, C, Bs, np.ascontiguousarray(delay_full, dtype=np.int32), n_t_out, out.data_ptr(),
-                                 torch.cuda.current_stream().cuda_stream)
+    # The C ABI takes a raw stream handle and treats 0 as "use the handle's own compute stream", which is not
+    # ordered after torch's legacy default stream: run the kernel on a real side stream fenced on both ends.
+    cur = torch.cuda.current_stream(full.device)
+    side = _side_stream(full.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        beamformer.dedisperse_device(full.data_ptr(), T, C, Bs, np.ascontiguousarray(delay_full, dtype=np.int32), n_t_out, out.data_ptr(),
+                                     side.cuda_stream)
+    cur.wait_stream(side)
+    full.record_stream(side)
+    out.record_stream(side)
     return out
+
+
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=key)
+    return _side_streams[key]

@@ -76,6 +76,36 @@ for c in range(2):
 ok &= bool(worst <= 1e-6)
 print("rank %d scaled-array shard (256 ant x 2048 beams) vs oracle: max rel %.2e" % (rank, worst), flush=True)
 Bs.close()
+
+# timing of the one exchange the path has, at the shard shape of configs[4]: [1024 times][256 ch][256 beams] per rank
+# -> all-to-all -> [1024][256*world][256/world], then 256 DM trials on the local beams (CUDA events, max over ranks)
+if world > 1:
+    Tt = 1024
+    pw = torch.rand((Tt, 256, 256), dtype=torch.float32, device="cuda")
+    dms_t = O.dm_trials(2000.0, 2048)[:256]
+    delay_t = O.dm_delays(dms_t, np.concatenate([D.subband_frequencies_ghz(D.subband_of_rank(r)) for r in range(world)])).astype(np.int32)
+    nto = Tt - int(delay_t.max())
+    times = []
+    ts = torch.cuda.Stream()
+    out_t = torch.empty((256, nto, 256 // world), dtype=torch.float32, device="cuda")
+    for rep in range(4):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        dist.barrier(); torch.cuda.synchronize()
+        with torch.cuda.stream(ts):
+            e[0].record()
+            full_t = D.freq_to_beam_all_to_all(pw)
+            e[1].record()
+            B.dedisperse_device(full_t.data_ptr(), Tt, 256 * world, 256 // world, delay_t, nto, out_t.data_ptr(), ts.cuda_stream)
+            e[2].record()
+        torch.cuda.synchronize()
+        times.append((e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])))
+    tt = torch.tensor(times[1:], dtype=torch.float64, device="cuda").min(dim=0).values
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        sent = Tt * 256 * 256 * 4 * (world - 1) / world
+        adds = 256.0 * 256 * world * (256 // world) * nto
+        print("rank 0 timing: transpose (2 permute copies + NCCL all_to_all_single) %.3f ms = %.1f GB/s sent per GPU; dedisperse 256 trials x %d ch x %d beams %.3f ms = %.2e adds/s per GPU, %.2e aggregate"
+              % (tt[0].item(), sent / tt[0].item() * 1e-6, 256 * world, 256 // world, tt[1].item(), adds / tt[1].item() * 1e3, world * adds / tt[1].item() * 1e3), flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 B.close()
