@@ -62,6 +62,15 @@ def test_fewer_beams(bf, oracle, n_beams):
     B.close()
 
 
+@pytest.mark.parametrize("n_beams", [64, 192])
+def test_odd_tile_counts_across_many_channels(bf, oracle, n_beams):
+    """1 or 3 M-tiles with one work item per channel and 2-3 channels per CTA: the two MMA issuers swap weight
+    tiles from channel to channel, and each must still see every weight tile of every channel arrive."""
+    B, w, packed = _rand_case(bf, False, 330, 1, seed=40 + n_beams, n_beams=n_beams)
+    _check_against_oracle(oracle, B, w, packed, B.beamform(packed))
+    B.close()
+
+
 @pytest.mark.parametrize("navg", [2, 4, 8, 32])
 def test_other_averaging_lengths(bf, oracle, navg):
     B, w, packed = _rand_case(bf, False, 2, 2 if navg < 32 else 1, seed=navg, n_averaging=navg)
@@ -75,6 +84,8 @@ def test_other_averaging_lengths(bf, oracle, navg):
     (128, 320, False, 2, 1),       # 2 k-blocks, odd number of M-tiles (the two MMA issuers alternate per item)
     (64, 512, False, 3, 2),        # more beams than the resident-weights kernel holds
     (192, 64, True, 2, 16),        # single M-tile: one issuer per item
+    (128, 64, False, 300, 1),      # single M-tile, 300 items on 148 CTAs: the issuers alternate items, both follow every B' phase
+    (64, 320, False, 310, 1),      # odd number of M-tiles and several items per CTA: issuer <-> stage pairing flips every item
 ])
 def test_streamed_weights_kernel_matches_oracle(bf, oracle, n_ant, n_beams, debug, n_chan, n_chunks):
     """fused_beamform_big.cu: up to 256 antennas / 4096 beams (weights streamed through shared memory)."""
