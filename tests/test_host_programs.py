@@ -67,6 +67,58 @@ int main(int argc, char** argv) {
         subprocess.call([_need("ringdb"), "-d", "-k", key])
 
 
+def test_observation_loop_state_machine(tmp_path):
+    """observation_loop.hh against stubbed tickets (no GPU): transfers are queued only while TQ-A < 4 and TQ-T < 2
+    (MAX_TOTAL_SEP / MAX_TRANSFER_SEP, beamformer.hh:117-118), analyses only while AQ < T, work retires in ticket
+    order, ring slots are the counters modulo 8, and the DEBUG run completes once every source had its chunk."""
+    src = tmp_path / "loop.cc"
+    src.write_text('''
+#include "observation_loop.hh"
+#include <cstdio>
+#include <cstdlib>
+static uint64_t done_t = 0, done_a = 0;                 // tickets below these values have completed
+extern "C" int dsabf_query_transfer(dsabf_handle*, uint64_t t) { return t < done_t ? 1 : 0; }
+extern "C" int dsabf_query_analysis(dsabf_handle*, uint64_t t) { return t < done_a ? 1 : 0; }
+#define REQUIRE(c) do { if (!(c)) { printf("FAILED line %d: %s\\n", __LINE__, #c); return 1; } } while (0)
+int main() {
+    beam::ObservationLoopState st(nullptr, 2, 4, 32, 8, true);
+    st.set_n_pt_sources(10 * 32);                         // 10 blocks of sources
+    uint64_t next_t = 0, next_a = 0; unsigned rng = 12345; int steps = 0;
+    while (!st.observations_complete()) {
+        REQUIRE(++steps < 100000);
+        rng = rng * 1664525u + 1013904223u;
+        if (st.ready_for_transfer() && !st.check_transfers_complete_debug()) {
+            REQUIRE(st.blocks_transfer_queue() - st.blocks_analyzed() < 4);
+            REQUIRE(st.blocks_transfer_queue() - st.blocks_transferred() < 2);
+            REQUIRE(st.next_transfer_slot() == (int)(st.blocks_transfer_queue() % 8));
+            st.transfer_enqueued(next_t++);
+        }
+        if (st.ready_for_analysis()) {
+            REQUIRE(st.blocks_analysis_queue() < st.blocks_transferred());
+            REQUIRE(st.next_analysis_slot() == (int)(st.blocks_analysis_queue() % 8));
+            REQUIRE(st.current_analysis_chunk(31) == st.blocks_analysis_queue() * 32 + 31);
+            st.analysis_enqueued(next_a++);
+        }
+        if ((rng >> 16) % 3 == 0 && done_t < next_t) done_t++;       // copies and kernels finish at random times, in order
+        if ((rng >> 20) % 4 == 0 && done_a < next_a) done_a++;
+        const uint64_t t0 = st.blocks_transferred(), a0 = st.blocks_analyzed();
+        st.check_transfer_events(false); st.check_analysis_events(false);
+        REQUIRE(st.blocks_transferred() == done_t && st.blocks_analyzed() == done_a);
+        REQUIRE(st.blocks_transferred() >= t0 && st.blocks_analyzed() >= a0);
+        REQUIRE(st.blocks_analyzed() <= st.blocks_analysis_queue() && st.blocks_analysis_queue() <= st.blocks_transferred());
+        REQUIRE(st.blocks_transferred() <= st.blocks_transfer_queue());
+    }
+    REQUIRE(st.blocks_analyzed() == 10 && st.blocks_transfer_queue() == 10 && st.transfers_complete());
+    printf("ok %d steps\\n", steps);
+    return 0;
+}
+''')
+    exe = tmp_path / "loop"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "dsabeamformer_b200", "host"), str(src), "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 def test_debug_program_matches_oracle_and_reference_binary(oracle, config_dir, tmp_path):
     """Config 1 end to end: bin/beam_debug on the linear array with 1024 sources writes bin/data.py
