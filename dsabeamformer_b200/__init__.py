@@ -75,6 +75,7 @@ def lib():
     L.dsabf_beamform_host.argtypes = [vp, vp, i, vp]
     L.dsabf_debug_voltages_host.argtypes = [vp, vp, i, vp, vp]
     L.dsabf_dedisperse_device.argtypes = [vp, vp, i, i, i, vp, i, i, vp, vp]
+    L.dsabf_transpose_pull_device.argtypes = [vp, vp, i, i, i, i, i, vp, vp]
     L.dsabf_dedisperse_host.argtypes = [vp, vp, i, i, i, vp, i, i, vp]
     L.dsabf_kernel_launches.argtypes = [vp]; L.dsabf_kernel_launches.restype = ctypes.c_uint64
     L.dsabf_fused_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i), i]
@@ -213,6 +214,12 @@ class Beamformer:
         delay = np.ascontiguousarray(delay, dtype=np.int32)
         _chk(lib().dsabf_dedisperse_device(self._h, ctypes.c_void_p(d_power_ptr), n_t, n_chan, n_beams, _ptr(delay),
                                            delay.shape[0], n_t_out, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(stream)))
+
+    def transpose_pull(self, peer_ptrs, rank, n_t, c_local, n_beams, d_full_ptr, stream=None):
+        """full[t][g*c_local+c][b] = power_g[t][c][rank*Bs+b], pulled from the peers' buffers over NVLink (exchange.cu)."""
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        _chk(lib().dsabf_transpose_pull_device(self._h, arr, len(peer_ptrs), rank, n_t, c_local, n_beams, ctypes.c_void_p(d_full_ptr),
+                                               ctypes.c_void_p(stream)))
 
     # -- introspection --
     @property

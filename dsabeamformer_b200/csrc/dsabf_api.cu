@@ -476,6 +476,19 @@ int dsabf_debug_trace(dsabf_handle *h, const void *d_packed, int n_chunks, float
 #endif
 }
 
+// ---- multi-GPU exchange ----------------------------------------------------------
+int dsabf_transpose_pull_device(dsabf_handle *h, const void *const *peer_power, int world, int rank, int n_t, int c_local, int n_beams,
+                                float *d_full, void *stream)
+{
+    if (!h || !peer_power || !d_full || world < 1 || rank < 0 || rank >= world || n_t < 0 || c_local < 0 || n_beams < 1)
+        return fail(DSABF_E_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->s_comp;
+    CK(dsabf::launch_transpose_pull(reinterpret_cast<const float *const *>(peer_power), world, rank, n_t, c_local, n_beams, d_full, h->num_sms, st));
+    h->launches++;
+    return 0;
+}
+
 // ---- dedispersion -------------------------------------------------------------
 int dsabf_dedisperse_device(dsabf_handle *h, const float *d_power, int n_t, int n_chan, int n_beams, const int32_t *h_delay, int n_dm,
                             int n_t_out, float *d_out, void *stream)

@@ -58,10 +58,42 @@ def freq_to_beam_all_to_all(power_local, group=None):
     return recv.permute(1, 0, 2, 3).reshape(T, world * C, Bs).contiguous()
 
 
-def dedisperse_full_band(beamformer, power_local, delay_full, n_t_out, group=None):
+def alloc_symmetric_power(n_t, c_local, n_beams, group=None):
+    """Power buffer [n_t][c_local][n_beams] that every rank of `group` can read directly over NVLink
+    (torch symmetric memory: plumbing only).  Returns (tensor, handle); handle.buffer_ptrs are the peers'
+    device pointers as mapped on this GPU.  Collective: every rank must call it with the same shape."""
+    import torch.distributed._symmetric_memory as symm_mem
+    t = symm_mem.empty((n_t, c_local, n_beams), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+    hdl = symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
+    return t, hdl
+
+
+def freq_to_beam_pull(beamformer, power_symm, hdl):
+    """Same result as freq_to_beam_all_to_all, but as ONE kernel of the library that pulls this rank's beams of
+    every peer's channels straight out of the peers' memory (csrc/exchange.cu) -- no permute copies, no NCCL.
+    power_symm / hdl come from alloc_symmetric_power.  Fenced by device-side barriers on the symmetric
+    allocation's signal pads: peers have finished writing before the pull, and are released after it."""
+    T, C, B = power_symm.shape
+    world, rank = hdl.world_size, hdl.rank
+    full = torch.empty((T, C * world, B // world), dtype=torch.float32, device=power_symm.device)
+    cur = torch.cuda.current_stream(power_symm.device)
+    side = _side_stream(power_symm.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        hdl.barrier(channel=0)
+        beamformer.transpose_pull(list(hdl.buffer_ptrs), rank, T, C, B, full.data_ptr(), side.cuda_stream)
+        hdl.barrier(channel=1)
+    cur.wait_stream(side)
+    full.record_stream(side)
+    return full
+
+
+def dedisperse_full_band(beamformer, power_local, delay_full, n_t_out, group=None, symm_handle=None):
     """Full-band incoherent dedispersion across ranks.  delay_full: int32 [n_dm][ch_local*world] in the
-    global channel order (rank-major).  Returns this rank's beams: [n_dm][n_t_out][B/world] (CUDA tensor)."""
-    full = freq_to_beam_all_to_all(power_local, group)
+    global channel order (rank-major).  Returns this rank's beams: [n_dm][n_t_out][B/world] (CUDA tensor).
+    With symm_handle (power_local allocated by alloc_symmetric_power) the exchange is the library's own
+    pull kernel over NVLink peer memory; otherwise NCCL all_to_all_single (gloo on CPU)."""
+    full = freq_to_beam_pull(beamformer, power_local, symm_handle) if symm_handle is not None else freq_to_beam_all_to_all(power_local, group)
     T, C, Bs = full.shape
     n_dm = delay_full.shape[0]
     out = torch.empty((n_dm, n_t_out, Bs), dtype=torch.float32, device=full.device)

@@ -136,6 +136,17 @@ int dsabf_dedisperse_device(dsabf_handle *h, const float *d_power, int n_t, int 
 int dsabf_dedisperse_host(dsabf_handle *h, const float *power, int n_t, int n_chan, int n_beams,
                           const int32_t *delay, int n_dm, int n_t_out, float *out);
 
+/* ---- multi-GPU exchange in front of full-band dedispersion (the reference has none: each
+ * `beam -g <k>` process sums only its own 256 channels, beamformer.cu:498-504) ----
+ * peer_power[g]: device pointer, valid on THIS GPU, to GPU g's power [n_t][c_local][n_beams] (peer-mapped
+ * memory, e.g. the buffer_ptrs of a torch symmetric-memory allocation; peer_power[rank] is the local one).
+ * d_full: [n_t][world*c_local][n_beams/world] float in local HBM:
+ *   full[t][g*c_local + c][b] = power_g[t][c][rank*(n_beams/world) + b]
+ * One kernel, loads over NVLink, no staging.  The caller fences: every peer has finished writing its power
+ * before the call, and nobody overwrites it until every rank's call has completed. */
+int dsabf_transpose_pull_device(dsabf_handle *h, const void *const *peer_power, int world, int rank, int n_t,
+                                int c_local, int n_beams, float *d_full, void *stream);
+
 /* ---- introspection ---- */
 /* number of this library's kernels launched on the handle since creation */
 uint64_t dsabf_kernel_launches(dsabf_handle *h);

@@ -60,6 +60,15 @@ rel = np.abs(ded - truth) / np.maximum(np.abs(truth), 1e-30)
 # float32 sums of world*256 positive terms in two different orders (kernel: 4-channel chunks; oracle: sequential):
 # typical difference sqrt(n)*2^-24, allowed n*1e-8
 ok &= bool(rel.max() <= max(5e-6, 1e-8 * full.shape[1]))
+try:        # same dedispersion with the exchange done by the library's NVLink pull kernel: bit-identical
+    sp, sh = D.alloc_symmetric_power(*d_power.shape)
+    sp.copy_(d_power)
+    ded2 = D.dedisperse_full_band(B, sp, delay, n_t_out, symm_handle=sh).cpu().numpy()
+    same = bool(np.array_equal(ded, ded2))
+    ok &= same
+    print("rank %d full-band dedispersion with the NVLink pull exchange identical to the NCCL one: %s" % (rank, same), flush=True)
+except Exception as ex:
+    print("rank %d symmetric memory unavailable (%s): NCCL exchange only" % (rank, str(ex).split("\n")[0][:120]), flush=True)
 print("rank %d full-band dedispersion (all-to-all + kernel) vs oracle: max rel %.2e" % (rank, rel.max()), flush=True)
 
 # BASELINE.json configs[3] (scaled array, frequency-sharded): 256 antennas x 2048 beams, this rank's channels
@@ -99,11 +108,36 @@ if world > 1:
             e[2].record()
         torch.cuda.synchronize()
         times.append((e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])))
+    # the same transpose as one kernel of ours over NVLink peer memory (csrc/exchange.cu)
+    pull_ms, pull_ok = float("nan"), True
+    try:
+        pws, hdl = D.alloc_symmetric_power(Tt, 256, 256)
+        pws.copy_(pw)
+        torch.cuda.synchronize(); dist.barrier()
+        ref_full = D.freq_to_beam_all_to_all(pw)
+        pt = []
+        for rep in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier(); torch.cuda.synchronize()
+            e0.record()
+            got_full = D.freq_to_beam_pull(B, pws, hdl)
+            e1.record(); torch.cuda.synchronize()
+            pt.append(e0.elapsed_time(e1))
+        pull_ok = bool(torch.equal(got_full, ref_full))
+        ok &= pull_ok
+        pull_ms = min(pt[1:])
+        print("rank %d NVLink pull transpose == NCCL all-to-all: %s (%.3f ms)" % (rank, pull_ok, pull_ms), flush=True)
+    except Exception as ex:                                     # symmetric memory unavailable on this box: NCCL path only
+        print("rank %d NVLink pull transpose unavailable: %s" % (rank, str(ex).split("\n")[0][:160]), flush=True)
     tt = torch.tensor(times[1:], dtype=torch.float64, device="cuda").min(dim=0).values
+    pm = torch.tensor([pull_ms if pull_ms == pull_ms else 0.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(pm, op=dist.ReduceOp.MAX)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     if rank == 0:
         sent = Tt * 256 * 256 * 4 * (world - 1) / world
         adds = 256.0 * 256 * world * (256 // world) * nto
+        if pm.item() > 0:
+            print("rank 0 timing: transpose as one pull kernel over NVLink peer memory %.3f ms = %.1f GB/s received per GPU" % (pm.item(), sent / pm.item() * 1e-6), flush=True)
         print("rank 0 timing: transpose (2 permute copies + NCCL all_to_all_single) %.3f ms = %.1f GB/s sent per GPU; dedisperse 256 trials x %d ch x %d beams %.3f ms = %.2e adds/s per GPU, %.2e aggregate"
               % (tt[0].item(), sent / tt[0].item() * 1e-6, 256 * world, 256 // world, tt[1].item(), adds / tt[1].item() * 1e3, world * adds / tt[1].item() * 1e3), flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
