@@ -76,6 +76,7 @@ def lib():
     L.dsabf_debug_voltages_host.argtypes = [vp, vp, i, vp, vp]
     L.dsabf_dedisperse_device.argtypes = [vp, vp, i, i, i, vp, i, i, vp, vp]
     L.dsabf_transpose_pull_device.argtypes = [vp, vp, i, i, i, i, i, vp, vp]
+    L.dsabf_dedisperse_single_peers_device.argtypes = [vp, vp, i, i, i, i, i, vp, i, vp, vp]
     L.dsabf_dedisperse_host.argtypes = [vp, vp, i, i, i, vp, i, i, vp]
     L.dsabf_kernel_launches.argtypes = [vp]; L.dsabf_kernel_launches.restype = ctypes.c_uint64
     L.dsabf_fused_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i), i]
@@ -220,6 +221,14 @@ class Beamformer:
         arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
         _chk(lib().dsabf_transpose_pull_device(self._h, arr, len(peer_ptrs), rank, n_t, c_local, n_beams, ctypes.c_void_p(d_full_ptr),
                                                ctypes.c_void_p(stream)))
+
+    def dedisperse_single_peers(self, peer_ptrs, rank, n_t, c_local, n_beams, delay, n_t_out, d_out_ptr, stream=None):
+        """One trial over the full band, channels read from the peers' buffers in place (exchange fused into the sum)."""
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        delay = np.ascontiguousarray(delay, dtype=np.int32).reshape(-1)
+        assert delay.shape[0] == len(peer_ptrs) * c_local
+        _chk(lib().dsabf_dedisperse_single_peers_device(self._h, arr, len(peer_ptrs), rank, n_t, c_local, n_beams, _ptr(delay), n_t_out,
+                                                        ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(stream)))
 
     # -- introspection --
     @property

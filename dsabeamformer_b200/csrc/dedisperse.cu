@@ -223,40 +223,58 @@ dedisperse_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_be
 // shared between trials, so skip shared memory.  Thread = (output time, 4 beams): 16-byte loads, coalesced across the
 // warp (512 contiguous bytes), 8 channels in flight per thread, channels added in order.  Pure streaming: HBM-bound.
 constexpr int DS_UNROLL = 8;
+constexpr int DS_MAX_SEG = 16;
+// The channel axis may be split into `n_seg` segments of c_seg channels living in different buffers -- the peers'
+// power buffers mapped over NVLink: full-band DM 0 across GPUs is then ONE kernel that reads every remote element
+// exactly once (exchange fused into the sum, nothing materialised).  Local case: one segment.
+struct Segments {
+    const float *p[DS_MAX_SEG];
+    int n_seg, c_seg;          // segments, channels per segment (c_seg % DS_UNROLL == 0 when n_seg > 1)
+    int row_floats, col_off;   // floats per (time, channel) row of a segment; first beam of this GPU's slice in it
+};
 // SPLIT > 1: small problems do not fill the machine with one thread per (time, 4 beams); SPLIT threads then share the
 // channel range of an item and slice 0 adds the partial sums in slice order (deterministic).
 template <int SPLIT>
 __global__ void __launch_bounds__(256)
-dedisperse_single_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_beams, const int32_t *__restrict__ delay, int n_t_out,
-                         float *__restrict__ out)
+dedisperse_single_kernel(Segments seg, int n_t, int n_chan, int n_beams, const int32_t *__restrict__ delay, int n_t_out, float *__restrict__ out)
 {
     constexpr int ITEMS = 256 / SPLIT;
     __shared__ float4 red[SPLIT > 1 ? SPLIT - 1 : 1][ITEMS];
-    const int b4 = n_beams >> 2;                                      // float4 per row
+    const int b4 = n_beams >> 2;                                      // float4 per output row
     const int li = threadIdx.x % ITEMS, slice = threadIdx.x / ITEMS;
     const long long idx = (long long)blockIdx.x * ITEMS + li;
     const bool live = idx < (long long)n_t_out * b4;
     const int t = live ? (int)(idx / b4) : 0, q = live ? (int)(idx - (long long)t * b4) : 0;
-    const float4 *src = reinterpret_cast<const float4 *>(power) + q;
+    const size_t rowf = (size_t)seg.row_floats;
+    const size_t qoff = (size_t)seg.col_off + 4 * (size_t)q;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int per = (n_chan + SPLIT - 1) / SPLIT;
+    int per = (n_chan + SPLIT - 1) / SPLIT;
+    per = (per + DS_UNROLL - 1) / DS_UNROLL * DS_UNROLL;              // slices start on an unroll boundary (never straddle a segment)
     int f = slice * per;
     const int f_end = min(n_chan, f + per);
+    auto ld = [](const float *a) {
+        float4 v;
+        asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a));
+        return v;
+    };
     if (live) {
         for (; f + DS_UNROLL <= f_end; f += DS_UNROLL) {
+            const int g = (seg.n_seg == 1) ? 0 : f / seg.c_seg;
+            const int c0 = f - g * seg.c_seg;
+            const float *base = seg.p[g];
             float4 v[DS_UNROLL];
 #pragma unroll
             for (int u = 0; u < DS_UNROLL; u++) {
                 const int tt = t + __ldg(delay + f + u);
-                v[u] = (tt < n_t) ? __ldcs(src + ((size_t)tt * n_chan + f + u) * b4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[u] = (tt < n_t) ? ld(base + ((size_t)tt * seg.c_seg + c0 + u) * rowf + qoff) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < DS_UNROLL; u++) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
         }
-        for (; f < f_end; f++) {
+        for (; f < f_end; f++) {                                      // tail: only in the one-segment case
             const int tt = t + __ldg(delay + f);
             if (tt < n_t) {
-                const float4 v = __ldcs(src + ((size_t)tt * n_chan + f) * b4);
+                const float4 v = ld(seg.p[0] + ((size_t)tt * seg.c_seg + f) * rowf + qoff);
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
         }
@@ -270,6 +288,16 @@ dedisperse_single_kernel(const float *__restrict__ power, int n_t, int n_chan, i
         }
     }
     if (live && slice == 0) reinterpret_cast<float4 *>(out)[(size_t)t * b4 + q] = acc;
+}
+
+cudaError_t launch_single(const Segments &seg, int n_t, int n_chan, int n_beams, const int32_t *d_delay, int n_t_out, float *d_out, cudaStream_t stream)
+{
+    const long long n = (long long)n_t_out * (n_beams >> 2);
+    // fewer than ~4 resident warps' worth of items per SM: split the channel range over 4 or 8 threads
+    if (n >= 65536) dedisperse_single_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(seg, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
+    else if (n >= 16384) dedisperse_single_kernel<4><<<(unsigned)((n + 63) / 64), 256, 0, stream>>>(seg, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
+    else dedisperse_single_kernel<8><<<(unsigned)((n + 31) / 32), 256, 0, stream>>>(seg, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
+    return cudaGetLastError();
 }
 
 template <int STAGES, int TSPLIT>
@@ -294,12 +322,9 @@ cudaError_t launch_dedisperse(const float *d_power, int n_t, int n_chan, int n_b
 {
     if (n_dm <= 0 || n_t_out <= 0) return cudaSuccess;
     if (n_dm == 1 && (n_beams & 3) == 0 && ((uintptr_t)d_power & 15) == 0 && ((uintptr_t)d_out & 15) == 0) {
-        const long long n = (long long)n_t_out * (n_beams >> 2);
-        // fewer than ~4 resident warps' worth of items per SM: split the channel range over 4 or 8 threads
-        if (n >= 65536) dedisperse_single_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
-        else if (n >= 16384) dedisperse_single_kernel<4><<<(unsigned)((n + 63) / 64), 256, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
-        else dedisperse_single_kernel<8><<<(unsigned)((n + 31) / 32), 256, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
-        return cudaGetLastError();
+        Segments seg{};
+        seg.p[0] = d_power; seg.n_seg = 1; seg.c_seg = n_chan; seg.row_floats = n_beams; seg.col_off = 0;
+        return launch_single(seg, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
     }
     // fewer than 8 trials: the 8 warps of a CTA split the output times instead of idling (tsplit = 8, 4, 2 for 1, 2, <=4 trials)
     const int tsplit = n_dm >= 5 ? 1 : (n_dm >= 3 ? 2 : (n_dm == 2 ? 4 : 8));
@@ -325,6 +350,24 @@ cudaError_t launch_dedisperse(const float *d_power, int n_t, int n_chan, int n_b
     default: return deep ? DD_LAUNCH(4, 8) : DD_LAUNCH(2, 8);
     }
 #undef DD_LAUNCH
+}
+
+// Full-band single-trial dedispersion with the channel axis spread over `world` peers' buffers
+// ([n_t][c_local][n_beams] each): this GPU sums its n_beams/world beams over all world*c_local channels.
+cudaError_t launch_dedisperse_single_peers(const float *const *peer_power, int world, int rank, int n_t, int c_local, int n_beams,
+                                           const int32_t *d_delay, int n_t_out, float *d_out, cudaStream_t stream)
+{
+    if (world < 1 || world > DS_MAX_SEG || rank < 0 || rank >= world || n_beams % world || (n_beams / world) % 4 || c_local % DS_UNROLL)
+        return cudaErrorInvalidValue;
+    if (n_t_out <= 0) return cudaSuccess;
+    Segments seg{};
+    for (int g = 0; g < world; g++) {
+        if (!peer_power[g] || ((uintptr_t)peer_power[g] & 15)) return cudaErrorInvalidValue;
+        seg.p[g] = peer_power[g];
+    }
+    const int bs = n_beams / world;
+    seg.n_seg = world; seg.c_seg = c_local; seg.row_floats = n_beams; seg.col_off = rank * bs;
+    return launch_single(seg, n_t, world * c_local, bs, d_delay, n_t_out, d_out, stream);
 }
 
 }  // namespace dsabf

@@ -63,6 +63,8 @@ struct dsabf_handle {
     uint8_t *d_wprep = nullptr;    // tensor-core layout
     int *d_bad = nullptr;
     long long *d_trace = nullptr;  // debug: clock64 trace buffer (dsabf_debug_trace)
+    int32_t *d_delay = nullptr; size_t delay_cap = 0;            // dedispersion delay table (grown on demand)
+    cudaEvent_t ev_delay = nullptr; bool delay_in_use = false;   // last kernel that read it
 
     std::vector<cudaEvent_t> ev_slot_h2d, ev_slot_comp, ev_slot_d2h;   // per ring slot
     std::vector<char> slot_has_h2d, slot_has_comp, slot_has_d2h;
@@ -140,6 +142,24 @@ int run_fused(dsabf_handle *h, const uint8_t *d_packed, int n_chunks, float *d_o
     else CK(dsabf::launch_fused_beamform_big(p, exact, h->num_sms, st));
     if (e1) CK(cudaEventRecord(e1, st));
     h->launches++;
+    return 0;
+}
+
+// Stream-ordered upload of a delay table into the handle's buffer: no host synchronisation, no allocation in the
+// steady state.  The buffer is reused, so the copy first waits (on the device) for the last kernel that read it.
+int upload_delays(dsabf_handle *h, const int32_t *h_delay, size_t n, cudaStream_t st)
+{
+    if (!h->ev_delay) CK(cudaEventCreateWithFlags(&h->ev_delay, cudaEventDisableTiming));
+    if (n > h->delay_cap) {
+        if (h->delay_in_use) CK(cudaEventSynchronize(h->ev_delay));
+        if (h->d_delay) CK(cudaFree(h->d_delay));
+        h->d_delay = nullptr; h->delay_cap = 0;
+        CK(cudaMalloc(&h->d_delay, sizeof(int32_t) * n));
+        h->delay_cap = n;
+        h->delay_in_use = false;
+    }
+    if (h->delay_in_use) CK(cudaStreamWaitEvent(st, h->ev_delay, 0));
+    CK(cudaMemcpyAsync(h->d_delay, h_delay, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
     return 0;
 }
 
@@ -261,6 +281,8 @@ int dsabf_destroy(dsabf_handle *h)
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     cudaFree(h->d_ring); cudaFree(h->d_out); cudaFree(h->d_ded); cudaFree(h->d_w); cudaFree(h->d_wprep); cudaFree(h->d_bad);
+    cudaFree(h->d_delay);
+    if (h->ev_delay) cudaEventDestroy(h->ev_delay);
     cudaFree(h->d_tmp_in); cudaFree(h->d_tmp_out);
     delete h;
     return 0;
@@ -499,13 +521,32 @@ int dsabf_dedisperse_device(dsabf_handle *h, const float *d_power, int n_t, int 
         if (h_delay[i] < 0) return fail(DSABF_E_INVALID, "negative delay");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->s_comp;
-    int32_t *d_delay = nullptr;
-    CK(cudaMalloc(&d_delay, sizeof(int32_t) * (size_t)n_dm * n_chan));
-    cudaError_t e = cudaMemcpyAsync(d_delay, h_delay, sizeof(int32_t) * (size_t)n_dm * n_chan, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = dsabf::launch_dedisperse(d_power, n_t, n_chan, n_beams, d_delay, n_dm, n_t_out, d_out, st);
-    if (e == cudaSuccess) { h->launches++; e = cudaStreamSynchronize(st); }
-    cudaFree(d_delay);
-    if (e != cudaSuccess) return fail((int)e, "dedisperse");
+    int rc = upload_delays(h, h_delay, (size_t)n_dm * n_chan, st);
+    if (rc) return rc;
+    CK(dsabf::launch_dedisperse(d_power, n_t, n_chan, n_beams, h->d_delay, n_dm, n_t_out, d_out, st));
+    h->launches++;
+    CK(cudaEventRecord(h->ev_delay, st));
+    h->delay_in_use = true;
+    return 0;
+}
+
+int dsabf_dedisperse_single_peers_device(dsabf_handle *h, const void *const *peer_power, int world, int rank, int n_t, int c_local, int n_beams,
+                                         const int32_t *h_delay, int n_t_out, float *d_out, void *stream)
+{
+    if (!h || !peer_power || !h_delay || !d_out || world < 1 || rank < 0 || rank >= world || n_t < 1 || c_local < 1 || n_beams < 4 || n_t_out < 1)
+        return fail(DSABF_E_INVALID, "bad argument");
+    const size_t n = (size_t)world * c_local;
+    for (size_t i = 0; i < n; i++)
+        if (h_delay[i] < 0) return fail(DSABF_E_INVALID, "negative delay");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->s_comp;
+    int rc = upload_delays(h, h_delay, n, st);
+    if (rc) return rc;
+    CK(dsabf::launch_dedisperse_single_peers(reinterpret_cast<const float *const *>(peer_power), world, rank, n_t, c_local, n_beams, h->d_delay,
+                                             n_t_out, d_out, st));
+    h->launches++;
+    CK(cudaEventRecord(h->ev_delay, st));
+    h->delay_in_use = true;
     return 0;
 }
 
@@ -522,6 +563,7 @@ int dsabf_dedisperse_host(dsabf_handle *h, const float *power, int n_t, int n_ch
     e = cudaMemcpy(d_in, power, in_b, cudaMemcpyHostToDevice);
     int rc = 0;
     if (e == cudaSuccess) rc = dsabf_dedisperse_device(h, d_in, n_t, n_chan, n_beams, delay, n_dm, n_t_out, d_o, nullptr);
+    if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(h->s_comp);      // dsabf_dedisperse_device is stream-ordered, not blocking
     if (e == cudaSuccess && !rc) e = cudaMemcpy(out, d_o, out_b, cudaMemcpyDeviceToHost);
     cudaFree(d_in);
     cudaFree(d_o);

@@ -29,6 +29,9 @@ cudaError_t launch_prep_weights(const int8_t *d_w, uint8_t *d_wprep, int n_chan,
                                 cudaStream_t stream);
 cudaError_t launch_dm0(const float *d_out, float *d_ded, int n_chunks, int n_out_per_chunk, int n_chan, int n_beams,
                        cudaStream_t stream);
+// dedisperse.cu: one trial over a channel axis spread across peers' buffers (exchange fused into the sum)
+cudaError_t launch_dedisperse_single_peers(const float *const *peer_power, int world, int rank, int n_t, int c_local, int n_beams,
+                                           const int32_t *d_delay, int n_t_out, float *d_out, cudaStream_t stream);
 // exchange.cu: frequency -> beam transpose pulled from peer GPUs' memory (NVLink), see the file header
 cudaError_t launch_transpose_pull(const float *const *peer_power, int world, int rank, int n_t, int c_local, int n_beams, float *d_full,
                                   int num_sms, cudaStream_t stream);

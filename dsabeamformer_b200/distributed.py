@@ -88,6 +88,25 @@ def freq_to_beam_pull(beamformer, power_symm, hdl):
     return full
 
 
+def dedisperse_single_full_band_fused(beamformer, power_symm, hdl, delay_1d, n_t_out):
+    """One trial (DM 0, or one delay curve: int32 [ch_local*world]) over the full band with the exchange FUSED into
+    the sum: the library's streaming kernel reads this rank's beams of every peer's channels in place over NVLink
+    (csrc/dedisperse.cu, dsabf_dedisperse_single_peers_device).  Returns [n_t_out][B/world]."""
+    T, C, B = power_symm.shape
+    world, rank = hdl.world_size, hdl.rank
+    out = torch.empty((n_t_out, B // world), dtype=torch.float32, device=power_symm.device)
+    cur = torch.cuda.current_stream(power_symm.device)
+    side = _side_stream(power_symm.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        hdl.barrier(channel=0)
+        beamformer.dedisperse_single_peers(list(hdl.buffer_ptrs), rank, T, C, B, delay_1d, n_t_out, out.data_ptr(), side.cuda_stream)
+        hdl.barrier(channel=1)
+    cur.wait_stream(side)
+    out.record_stream(side)
+    return out
+
+
 def dedisperse_full_band(beamformer, power_local, delay_full, n_t_out, group=None, symm_handle=None):
     """Full-band incoherent dedispersion across ranks.  delay_full: int32 [n_dm][ch_local*world] in the
     global channel order (rank-major).  Returns this rank's beams: [n_dm][n_t_out][B/world] (CUDA tensor).

@@ -130,7 +130,9 @@ int dsabf_debug_voltages_host(dsabf_handle *h, const void *packed, int n_chunks,
  * DM > 0 per sandbox/Dispersion Theory.ipynb cells 2,5) ----
  * d_power: [n_t][n_chan][n_beams] float in HBM; h_delay: [n_dm][n_chan] int32 >= 0
  * (host); d_out: [n_dm][n_t_out][n_beams] float in HBM:
- *   out[d][t][b] = sum_f power[t + delay[d][f]][f][b]   (terms with t+delay >= n_t dropped) */
+ *   out[d][t][b] = sum_f power[t + delay[d][f]][f][b]   (terms with t+delay >= n_t dropped)
+ * dsabf_dedisperse_device is stream-ordered (returns after enqueueing; h_delay may be reused at once);
+ * stream NULL = the handle's compute stream, which dsabf_sync() drains. */
 int dsabf_dedisperse_device(dsabf_handle *h, const float *d_power, int n_t, int n_chan, int n_beams,
                             const int32_t *h_delay, int n_dm, int n_t_out, float *d_out, void *stream);
 int dsabf_dedisperse_host(dsabf_handle *h, const float *power, int n_t, int n_chan, int n_beams,
@@ -146,6 +148,14 @@ int dsabf_dedisperse_host(dsabf_handle *h, const float *power, int n_t, int n_ch
  * before the call, and nobody overwrites it until every rank's call has completed. */
 int dsabf_transpose_pull_device(dsabf_handle *h, const void *const *peer_power, int world, int rank, int n_t,
                                 int c_local, int n_beams, float *d_full, void *stream);
+
+/* Full-band single-trial dedispersion (DM 0 = the DEBUG cublasSgemv over ALL sub-bands, or any one delay curve)
+ * fused with the exchange: this GPU's n_beams/world beams summed over the world*c_local channels that live in the
+ * peers' buffers, every remote element read once over NVLink, nothing materialised.
+ * h_delay: [world*c_local] int32 (host), global channel order; d_out: [n_t_out][n_beams/world] float. */
+int dsabf_dedisperse_single_peers_device(dsabf_handle *h, const void *const *peer_power, int world, int rank, int n_t,
+                                         int c_local, int n_beams, const int32_t *h_delay, int n_t_out, float *d_out,
+                                         void *stream);
 
 /* ---- introspection ---- */
 /* number of this library's kernels launched on the handle since creation */

@@ -127,6 +127,20 @@ if world > 1:
         ok &= pull_ok
         pull_ms = min(pt[1:])
         print("rank %d NVLink pull transpose == NCCL all-to-all: %s (%.3f ms)" % (rank, pull_ok, pull_ms), flush=True)
+        # full-band DM 0 (the reference's gemv over ALL sub-bands): exchange fused into the streaming sum vs transpose-then-sum
+        zero = np.zeros((1, 256 * world), dtype=np.int32)
+        two_step = D.dedisperse_full_band(B, pws, zero, Tt, symm_handle=hdl)[0]
+        ft = []
+        for rep in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier(); torch.cuda.synchronize()
+            e0.record()
+            fused = D.dedisperse_single_full_band_fused(B, pws, hdl, zero[0], Tt)
+            e1.record(); torch.cuda.synchronize()
+            ft.append(e0.elapsed_time(e1))
+        same0 = bool(torch.equal(fused, two_step))
+        ok &= same0
+        print("rank %d full-band DM 0 fused over NVLink == transpose + sum: %s (%.3f ms)" % (rank, same0, min(ft[1:])), flush=True)
     except Exception as ex:                                     # symmetric memory unavailable on this box: NCCL path only
         print("rank %d NVLink pull transpose unavailable: %s" % (rank, str(ex).split("\n")[0][:160]), flush=True)
     tt = torch.tensor(times[1:], dtype=torch.float64, device="cuda").min(dim=0).values
