@@ -155,8 +155,9 @@ int main(int argc, char *argv[])
     Stopwatch sw{h, {}};
     sw.start();
     float observation_time_ms = 0;
-    uint64_t blocks_read = 0;
-    (void)blocks_read;
+#if !BEAM_DEBUG
+    uint64_t blocks_read = 0;   // data blocks taken from the ring after the burn-in
+#endif
 
     while (!obs.observations_complete()) {
         if (verbose) { std::cout << "##########################################" << std::endl; std::cout << obs << std::endl; }
@@ -237,6 +238,7 @@ int main(int argc, char *argv[])
         std::cout << "Code produced outputs for " << obs.current_transfer_chunk() * cfg.n_outputs_per_chunk << " data chunks.\n";
         std::cout << "Time per data chunk: " << observation_time_ms / (obs.current_transfer_chunk() * cfg.n_outputs_per_chunk) << " milliseconds.\n";
         std::cout << "Approximate datarate: " << (double)dada.get_block_size() * obs.blocks_transfer_queue() / observation_time_ms / 1e6 << "GB/s" << std::endl;
+        std::cout << "Blocks read from the ring after the burn-in: " << blocks_read << std::endl;
     }
 #endif
     CHK(dsabf_sync(h));
