@@ -42,7 +42,7 @@ struct __align__(1024) SmemBig {
     uint8_t a[kARing][kATileBytes];      //  96 KB  streamed weight tiles
     uint8_t b[kMaxKB][kBTileBytes];      // 128 KB  unpacked voltages of the current item, one tile per k-block
     uint64_t a_full[kARing], a_empty[kARing];
-    uint64_t b_full, b_empty;
+    uint64_t b_full[2], b_empty[2];      // B' is double-buffered when it fits (<= 2 k-blocks), else one buffer
     uint64_t acc_full[2], acc_empty[2];
     uint64_t turn[2];                    // baton between the two MMA issuers
     uint32_t tmem_base;
@@ -80,8 +80,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kARing; i++) { mbar_init(&sm.a_full[i], 1); mbar_init(&sm.a_empty[i], 1); }
-        mbar_init(&sm.b_full, kNumUnpackWarps);
-        mbar_init(&sm.b_empty, mt == 1 ? 1 : 2);                 // one commit per MMA issuer
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&sm.b_full[i], kNumUnpackWarps);
+            mbar_init(&sm.b_empty[i], mt == 1 ? 1 : 2);          // one commit per MMA issuer that multiplied the item
+        }
         for (int i = 0; i < 2; i++) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], kNumEpiWarps); mbar_init(&sm.turn[i], 1); }
         fence_mbar_init();
     }
@@ -94,6 +96,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
     const uint32_t a_smem = sbase + (uint32_t)offsetof(SmemBig, a), b_smem = sbase + (uint32_t)offsetof(SmemBig, b);
     const uint32_t bar_a_full = sbase + (uint32_t)offsetof(SmemBig, a_full), bar_a_empty = sbase + (uint32_t)offsetof(SmemBig, a_empty);
     const uint32_t bar_b_full = sbase + (uint32_t)offsetof(SmemBig, b_full), bar_b_empty = sbase + (uint32_t)offsetof(SmemBig, b_empty);
+    // B' buffers: item `it` uses buffer it % nbuf, fill number it / nbuf of that buffer
+    const int nbuf_log2 = (kb_n <= 2) ? 1 : 0;
+    const uint32_t b_buf_bytes = (uint32_t)kb_n * kBTileBytes;
     const uint32_t bar_acc_full = sbase + (uint32_t)offsetof(SmemBig, acc_full), bar_acc_empty = sbase + (uint32_t)offsetof(SmemBig, acc_empty);
     const uint32_t bar_turn = sbase + (uint32_t)offsetof(SmemBig, turn);
 
@@ -120,7 +125,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
             uint32_t acc_cnt = 0, use = 0;                       // use: M-tiles this issuer has multiplied
             for (int item = item_begin, it = 0; item < item_end; item += item_step, it++) {
                 // every issuer observes every phase of b_full, also for an item it has no M-tile of (n_beams = 64)
-                mbar_wait(bar_b_full, it & 1, 3);
+                const uint32_t bbuf = it & ((1 << nbuf_log2) - 1);
+                mbar_wait(bar_b_full + 8 * bbuf, (it >> nbuf_log2) & 1, 3);
                 bool touched = false;
                 for (int m = 0; m < mt; m++, acc_cnt++) {
                     if ((int)(acc_cnt & 1) != me) continue;
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
                         if (kb == kb_n - 1) mbar_arrive(bar_turn + 8 * (me ^ 1));      // pass the baton
                         tc_fence_after();
                         const uint64_t adesc = make_desc_k_sw128(a_smem + slot * kATileBytes);
-                        const uint64_t bdesc = make_desc_k_sw128(b_smem + kb * kBTileBytes);
+                        const uint64_t bdesc = make_desc_k_sw128(b_smem + bbuf * b_buf_bytes + kb * kBTileBytes);
 #pragma unroll
                         for (int k = 0; k < kRowBytes / 32; k++)
                             mma_i8_ss(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1 : 0);
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
                     tc_commit(bar_acc_full + 8 * me);
                     use++;
                 }
-                if (touched) tc_commit(bar_b_empty);
+                if (touched) tc_commit(bar_b_empty + 8 * bbuf);
             }
         }
     } else if (warp < kEpiWarp0) {
@@ -159,7 +165,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
         const uint32_t st_im = r * 128 + (((c + 4) ^ r) << 4);
         for (int item = item_begin, it = 0; item < item_end; item += item_step, it++) {
             const int f = item / g.n_tiles, t = item - f * g.n_tiles;
-            mbar_wait<200>(bar_b_empty, (it & 1) ^ 1, 7);
+            const uint32_t bbuf = it & ((1 << nbuf_log2) - 1);
+            mbar_wait<200>(bar_b_empty + 8 * bbuf, ((it >> nbuf_log2) & 1) ^ 1, 7);
 #pragma unroll 1
             for (int i = 0; i < (kTileN / 8) / kNumUnpackWarps; i += 2) {
                 uint4 v[2][kMaxKB];
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
                             re.y = w.y & 0xF0F0F0F0u; im.y = (w.y << 4) & 0xF0F0F0F0u;
                             re.z = w.z & 0xF0F0F0F0u; im.z = (w.z << 4) & 0xF0F0F0F0u;
                             re.w = w.w & 0xF0F0F0F0u; im.w = (w.w << 4) & 0xF0F0F0F0u;
-                            const uint32_t dst = b_smem + kb * kBTileBytes + grp * 1024;
+                            const uint32_t dst = b_smem + bbuf * b_buf_bytes + kb * kBTileBytes + grp * 1024;
                             sts128(dst + st_re, re);
                             sts128(dst + st_im, im);
                         }
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_b_full);
+            if (lane == 0) mbar_arrive(bar_b_full + 8 * bbuf);
         }
     } else {
         // ================= epilogue (identical to fused_beamform.cu) =================
