@@ -203,6 +203,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_b_full + 8 * bbuf);
+            // The next item's columns are loaded only after the MMAs of an item in between have drained their B'
+            // buffer; pull them into L2 now so that those loads -- the bubble of a single-buffered B' -- do not
+            // pay DRAM latency.
+            const int item2 = item + item_step;
+            if (item2 < item_end) {
+                const int f2 = item2 / g.n_tiles, t2 = item2 - f2 * g.n_tiles;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int cg = t2 * kTileN + h * (kTileN / 2) + uw * 32 + lane;
+                    if (cg < g.n_cols_total) {
+                        const int chunk = cg / g.cpc, c_in = cg - chunk * g.cpc;
+                        const uint8_t *row = p.packed + ((((size_t)chunk * g.n_chan + f2) * g.cpc + c_in) * p.n_ant);
+                        for (int o = 0; o < p.n_ant; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+                    }
+                }
+            }
         }
     } else {
         // ================= epilogue (identical to fused_beamform.cu) =================
