@@ -15,6 +15,7 @@
 
 #include "beam_config.hh"
 #include "observation_loop.hh"
+#include "dada_ring.hh"
 #if BEAM_DEBUG
 #include "test_data_generator.hh"
 #else
@@ -131,9 +132,30 @@ int main(int argc, char *argv[])
         CHK(dsabf_set_weights(h, w.data()));
     }
 
-    // final data product buffer (pinned, caller-owned): two blocks of power, used alternately
+    // final data product buffer (pinned, caller-owned): kOutBufs blocks of power used in turn.  A block's buffer is
+    // reused by block k + kOutBufs, which cannot be queued before block k was seen complete (TQ - A < MAX_TOTAL_SEP).
+    constexpr int kOutBufs = 4;
+    static_assert(kOutBufs >= kMaxTotalSep, "output buffers must cover the blocks in flight");
+    const size_t out_block_floats = chunk_out * cpb;
     float *beam_out = nullptr;
-    CUCHK(cudaHostAlloc((void **)&beam_out, sizeof(float) * chunk_out * cpb * 2, 0));
+    CUCHK(cudaHostAlloc((void **)&beam_out, sizeof(float) * out_block_floats * kOutBufs, 0));
+
+    // Output sink (the reference drops beam_out, beamformer.cu:485-488): with DSABF_OUT_KEY=<hex>
+    // every finished block of power, float [out_time][channel][beam], is appended to that PSRDADA-style ring for the
+    // next stage (dedispersion / search) to read.
+    DadaRing sink;
+    bool have_sink = false;
+    uint64_t blocks_sunk = 0;
+    if (const char *k = getenv("DSABF_OUT_KEY")) {
+        unsigned out_key = 0;
+        if (sscanf(k, "%x", &out_key) != 1 || !sink.connect(out_key)) { fprintf(stderr, "beam: could not connect to output ring %s\n", k); return EXIT_FAILURE; }
+        if (sink.bufsz() < sizeof(float) * out_block_floats) { fprintf(stderr, "beam: output ring blocks are smaller than %zu bytes\n", sizeof(float) * out_block_floats); return EXIT_FAILURE; }
+        char hdr[256];
+        const int n = snprintf(hdr, sizeof(hdr), "HDR_VERSION 1.0\nINSTRUMENT DSAX\nDTYPE float32\nORDER TFB\nNBEAM %d\nNCHAN %d\nNTIME %d\nSUBBAND %d\n",
+                               cfg.n_beams, cfg.n_channels, cfg.n_outputs_per_chunk * cpb, gpu);
+        sink.write_header(hdr, (size_t)n + 1);
+        have_sink = true;
+    }
 
     ObservationLoopState obs(h, kMaxTransferSep, kMaxTotalSep, cpb, cfg.n_ring_slots, debug);
 #if BEAM_DEBUG
@@ -204,7 +226,7 @@ int main(int argc, char *argv[])
         if (obs.ready_for_analysis()) {
             const uint64_t first_chunk = obs.current_analysis_chunk(0);
             if (verbose) std::cout << "Queueing Beamforming. Start Dir = " << first_chunk << std::endl;
-            float *out_host = beam_out + (obs.blocks_analysis_queue() & 1) * chunk_out * cpb;
+            float *out_host = beam_out + (obs.blocks_analysis_queue() % kOutBufs) * out_block_floats;
             uint64_t ticket = 0;
 #if BEAM_DEBUG
             long n_valid = (long)n_pt_sources - (long)first_chunk;     // `current_gemm < n_pt_sources` guard (:492)
@@ -220,10 +242,17 @@ int main(int argc, char *argv[])
             obs.analysis_enqueued(ticket);
         }
         obs.check_analysis_events(verbose);
+        while (have_sink && blocks_sunk < obs.blocks_analyzed()) {       // hand finished blocks to the next stage, in order
+            char *dst = sink.open_block_write();
+            memcpy(dst, beam_out + (blocks_sunk % kOutBufs) * out_block_floats, sizeof(float) * out_block_floats);
+            sink.close_block_write(sizeof(float) * out_block_floats);
+            blocks_sunk++;
+        }
 #if !BEAM_DEBUG
         dada.retire(h);
 #endif
     }
+    if (have_sink) { sink.mark_eod(); sink.disconnect(); }
 
     // ---- report (beamformer.cu:539-557) ----
     observation_time_ms += sw.stop_ms();

@@ -192,3 +192,64 @@ def test_observation_program_streams_from_ring(config_dir):
         assert m and int(m.group(1)) == 15 * 32 * 8          # 40 blocks - 25 burn-in = 15 blocks x 32 chunks x 8 outputs
     finally:
         subprocess.call([_need("ringdb"), "-d", "-k", key])
+
+
+def _splitmix64_block(n_bytes, seed=0xD5A):
+    """the junk block of bin/junkdb (ring_tools.cc): splitmix64 stream, little-endian, vectorised"""
+    with np.errstate(over="ignore"):
+        i = np.arange(1, n_bytes // 8 + 1, dtype=np.uint64)
+        z = np.uint64(seed) + i * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z.view(np.uint8)
+
+
+@pytest.mark.gpu
+def test_observation_program_output_sink(bf, oracle, config_dir, tmp_path):
+    """with DSABF_OUT_KEY bin/beam appends every finished block of power (float [time][chan][beam],
+    64 MiB) to an output ring.  Three data blocks after the burn-in; the blocks read back must equal what the library
+    computes for the same ring input (junkdb's splitmix64 block, rotated by (block % 16) * 4096 bytes)."""
+    reader = tmp_path / "dump.cc"
+    reader.write_text('''
+#include "dada_ring.hh"
+#include <cstdio>
+int main(int argc, char** argv) {
+    unsigned key; sscanf(argv[1], "%x", &key);
+    beam::DadaRing r; if (!r.connect(key)) return 2;
+    uint64_t hs; const char* h = r.read_header(&hs); printf("header: %.120s\\n", h);
+    uint64_t n = 0, bytes, id;
+    for (;;) { char* b = r.open_block_read(&bytes, &id); if (bytes == 0) break;
+        char name[256]; snprintf(name, sizeof name, "%s/block%llu.bin", argv[2], (unsigned long long)n);
+        FILE* f = fopen(name, "wb"); fwrite(b, 1, bytes, f); fclose(f); n++; r.close_block_read(); }
+    printf("blocks %llu\\n", (unsigned long long)n); return 0; }
+''')
+    exe = tmp_path / "dump"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "dsabeamformer_b200", "host"), str(reader), "-o", str(exe), "-lrt"])
+    key_in, key_out = "%x" % (0xd000 + os.getpid() % 4096), "%x" % (0xe000 + os.getpid() % 4096)
+    subprocess.check_call([_need("ringdb"), "-k", key_in, "-n", "8", "-b", "134217728"])
+    subprocess.check_call([_need("ringdb"), "-k", key_out, "-n", "4", "-b", "67108864"])
+    try:
+        w = subprocess.Popen([_need("junkdb"), "-k", key_in, "-r", "0", "-n", "28", os.path.join(config_dir, "correlator_header_dsaX.txt")],
+                             stdout=subprocess.PIPE, text=True)
+        pfile, dfile = os.path.join(config_dir, "grid_positions.txt"), os.path.join(config_dir, "grid_beam_directions.txt")
+        r = subprocess.run([_need("beam"), "-k", key_in, "-c", "-1", "-g", "2", "-p", pfile, "-d", dfile], capture_output=True, text=True,
+                           timeout=600, env=dict(os.environ, DSABF_OUT_KEY=key_out))
+        w.wait(timeout=60)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        d = subprocess.run([str(exe), key_out, str(tmp_path)], capture_output=True, text=True, timeout=120)
+        assert d.returncode == 0 and "blocks 3" in d.stdout, d.stdout + d.stderr
+        assert "ORDER TFB" in d.stdout and "NBEAM 256" in d.stdout and "SUBBAND 2" in d.stdout
+    finally:
+        subprocess.call([_need("ringdb"), "-d", "-k", key_in])
+        subprocess.call([_need("ringdb"), "-d", "-k", key_out])
+    junk = _splitmix64_block(134217728)
+    pos = oracle.read_positions(pfile); dirs = oracle.read_directions(dfile, 256)
+    B = bf.Beamformer(debug=False)
+    B.set_weights(bf.compute_weights(pos, dirs, 2))
+    for i, blk in ((0, 25), (2, 27)):                      # first and last data block (ring blocks 25 and 27 after the burn-in)
+        packed = np.roll(junk, -((blk % 16) * 4096)).reshape(32, 256, 256, 64)
+        got = np.fromfile(tmp_path / ("block%d.bin" % i), dtype=np.float32).reshape(256, 256, 256)
+        assert np.array_equal(got, B.beamform(packed)), i
+    B.close()
+
