@@ -305,12 +305,10 @@ cudaError_t launch_stages(dim3 grid, const float *d_power, int n_t, int n_chan, 
                           float *d_out, cudaStream_t stream)
 {
     constexpr size_t smem = sizeof(float) * STAGES * DD_FC * DD_WIN * DD_BB + STAGES * sizeof(ChunkMeta);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dedisperse_kernel<STAGES, TSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // The attribute belongs to the (function, device) pair and a process may hold handles on several GPUs from
+    // several threads: set it on every launch for the current device (a cheap driver call) instead of caching it.
+    cudaError_t e = cudaFuncSetAttribute(dedisperse_kernel<STAGES, TSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     dedisperse_kernel<STAGES, TSPLIT><<<grid, DD_THREADS, smem, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_dm, n_t_out, d_out);
     return cudaGetLastError();
 }
@@ -333,13 +331,10 @@ cudaError_t launch_dedisperse(const float *d_power, int n_t, int n_chan, int n_b
     if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidValue;
     // Few CTAs (few DM trials): each walks all channels serially and the kernel is bound by load latency, so
     // keep 3 chunks (48 KB) in flight per CTA; many CTAs: 2 stages and 3 CTAs per SM hide it better.
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-    }
+    int num_sms = 0, dev = 0;       // of the current device (per call: handles on different GPUs may share this process)
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
     const long long n_cta = (long long)grid.x * grid.y * grid.z;
     const bool deep = n_cta <= 2LL * num_sms;
 #define DD_LAUNCH(S, T) launch_stages<S, T>(grid, d_power, n_t, n_chan, n_beams, d_delay, n_dm, n_t_out, d_out, stream)

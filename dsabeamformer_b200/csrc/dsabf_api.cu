@@ -429,6 +429,8 @@ int dsabf_sync(dsabf_handle *h)
 int dsabf_beamform_device(dsabf_handle *h, const void *d_packed, int n_chunks, float *d_out, void *stream)
 {
     if (!h || !d_packed || !d_out || n_chunks < 0) return fail(DSABF_E_INVALID, "bad argument");
+    // bulk copies (resident kernel) and 16-byte vector loads (streamed kernel) read d_packed; float stores are scalar
+    if (((uintptr_t)d_packed & 15) || ((uintptr_t)d_out & 3)) return fail(DSABF_E_INVALID, "d_packed must be 16-byte aligned, d_out 4-byte aligned");
     CK(cudaSetDevice(h->device));
     return run_fused(h, (const uint8_t *)d_packed, n_chunks, d_out, nullptr, nullptr, h->cfg.exact_power != 0,
                      stream ? (cudaStream_t)stream : h->s_comp);
@@ -519,6 +521,10 @@ int dsabf_dedisperse_device(dsabf_handle *h, const float *d_power, int n_t, int 
         return fail(DSABF_E_INVALID, "bad argument");
     for (size_t i = 0; i < (size_t)n_dm * n_chan; i++)
         if (h_delay[i] < 0) return fail(DSABF_E_INVALID, "negative delay");
+    // with n_beams a multiple of 4 the staged kernel moves 16-byte pieces of the rows with cp.async (other beam counts
+    // take its scalar path; the single-trial kernel checks its own alignment and falls back to the staged one)
+    if ((n_beams & 3) == 0 && ((uintptr_t)d_power & 15)) return fail(DSABF_E_INVALID, "d_power must be 16-byte aligned");
+    if (((uintptr_t)d_power & 3) || ((uintptr_t)d_out & 3)) return fail(DSABF_E_INVALID, "d_power and d_out must be 4-byte aligned");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->s_comp;
     int rc = upload_delays(h, h_delay, (size_t)n_dm * n_chan, st);

@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
                 ctx.pp = pp_item;
                 epi_block<G, EXACT, 0>(ctx, va);
                 epi_block<G, EXACT, 1>(ctx, vb);
+                epi_finish<G, EXACT>(ctx);
                 out_item += 64;
                 if (EXACT) { if (pp_item) pp_item += 64; }
             }
@@ -289,12 +290,10 @@ template <int G, int MODE>
 cudaError_t launch_one(const FusedParams &p, int grid, cudaStream_t stream)
 {
     const size_t smem = sizeof(SmemBig) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_beamform_big_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // The attribute belongs to the (function, device) pair and a process may hold handles on several GPUs from
+    // several threads: set it on every launch for the current device (a cheap driver call) instead of caching it.
+    cudaError_t e = cudaFuncSetAttribute(fused_beamform_big_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     fused_beamform_big_kernel<G, MODE><<<grid, kThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }

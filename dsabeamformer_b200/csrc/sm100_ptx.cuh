@@ -206,6 +206,17 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32])
                  : "memory");
 }
 
+// Wait for two loads issued earlier with tmem_ld_32x32: the wait carries the first register set, an empty
+// volatile statement right behind it the second, so that no consumer of either can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld_wait2(uint32_t (&a)[32], uint32_t (&b)[32])
+{
+    tmem_ld_wait(a);
+    asm volatile(""
+                 : "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]), "+r"(b[16]), "+r"(b[17]), "+r"(b[18]), "+r"(b[19]), "+r"(b[20]), "+r"(b[21]), "+r"(b[22]), "+r"(b[23]), "+r"(b[24]), "+r"(b[25]), "+r"(b[26]), "+r"(b[27]), "+r"(b[28]), "+r"(b[29]), "+r"(b[30]), "+r"(b[31])
+                 :
+                 : "memory");
+}
+
 // Two adjacent 32-column loads and the wait in ONE asm statement: one TMEM address operand (one R2UR instead
 // of two), and the consumers of a[]/b[] cannot be scheduled above the wait because the registers are
 // outputs of the statement that contains it.

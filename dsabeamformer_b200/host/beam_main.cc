@@ -15,7 +15,8 @@
 
 #include "beam_config.hh"
 #include "observation_loop.hh"
-#include "dada_ring.hh"
+#include "dada_hdu.h"          // PSRDADA API: $(PSRDADA_INC) = host/psrdada_compat + the shim library, or the real thing
+#include "ascii_header.h"
 #if BEAM_DEBUG
 #include "test_data_generator.hh"
 #else
@@ -119,7 +120,8 @@ int main(int argc, char *argv[])
     CUCHK(cudaHostAlloc((void **)&dedispersed_out, sizeof(float) * (size_t)cfg.n_beams * n_pt_sources, 0));
     memset(dedispersed_out, 0, sizeof(float) * (size_t)cfg.n_beams * n_pt_sources);
 #else
-    DadaHandler dada("beam", core, in_key, block_bytes, verbose);
+    DadaHandler dada("beam", core, (key_t)in_key, block_bytes, verbose);
+    if (dada.ring_blocks() < 2) { fprintf(stderr, "beam: the input ring needs at least 2 blocks\n"); return EXIT_FAILURE; }
 #endif
 
     // steering weights: beamformer.cu:230-241 behind dsabf_compute_weights
@@ -143,25 +145,48 @@ int main(int argc, char *argv[])
     // Output sink (the reference drops beam_out, beamformer.cu:485-488): with DSABF_OUT_KEY=<hex>
     // every finished block of power, float [out_time][channel][beam], is appended to that PSRDADA-style ring for the
     // next stage (dedispersion / search) to read.
-    DadaRing sink;
-    bool have_sink = false;
+    dada_hdu_t *sink = nullptr;
+    multilog_t *sink_log = nullptr;
     uint64_t blocks_sunk = 0;
     if (const char *k = getenv("DSABF_OUT_KEY")) {
         unsigned out_key = 0;
-        if (sscanf(k, "%x", &out_key) != 1 || !sink.connect(out_key)) { fprintf(stderr, "beam: could not connect to output ring %s\n", k); return EXIT_FAILURE; }
-        if (sink.bufsz() < sizeof(float) * out_block_floats) { fprintf(stderr, "beam: output ring blocks are smaller than %zu bytes\n", sizeof(float) * out_block_floats); return EXIT_FAILURE; }
-        char hdr[256];
-        const int n = snprintf(hdr, sizeof(hdr), "HDR_VERSION 1.0\nINSTRUMENT DSAX\nDTYPE float32\nORDER TFB\nNBEAM %d\nNCHAN %d\nNTIME %d\nSUBBAND %d\n",
-                               cfg.n_beams, cfg.n_channels, cfg.n_outputs_per_chunk * cpb, gpu);
-        sink.write_header(hdr, (size_t)n + 1);
-        have_sink = true;
+        sink_log = multilog_open("beam_out", 0);
+        multilog_add(sink_log, stderr);
+        sink = dada_hdu_create(sink_log);
+        if (sscanf(k, "%x", &out_key) == 1) dada_hdu_set_key(sink, (key_t)out_key);
+        if (sscanf(k, "%x", &out_key) != 1 || dada_hdu_connect(sink) < 0 || dada_hdu_lock_write(sink) < 0) {
+            fprintf(stderr, "beam: could not connect to output ring %s\n", k);
+            return EXIT_FAILURE;
+        }
+        if (ipcbuf_get_bufsz((ipcbuf_t *)sink->data_block) < sizeof(float) * out_block_floats) {
+            fprintf(stderr, "beam: output ring blocks are smaller than %zu bytes\n", sizeof(float) * out_block_floats);
+            return EXIT_FAILURE;
+        }
+        const uint64_t hsz = ipcbuf_get_bufsz(sink->header_block);
+        char *hdr = ipcbuf_get_next_write(sink->header_block);
+        memset(hdr, 0, hsz);
+        ascii_header_set(hdr, "HDR_VERSION", "%s", "1.0");
+        ascii_header_set(hdr, "INSTRUMENT", "%s", "DSAX");
+        ascii_header_set(hdr, "DTYPE", "%s", "float32");
+        ascii_header_set(hdr, "ORDER", "%s", "TFB");
+        ascii_header_set(hdr, "NBEAM", "%d", cfg.n_beams);
+        ascii_header_set(hdr, "NCHAN", "%d", cfg.n_channels);
+        ascii_header_set(hdr, "NTIME", "%d", cfg.n_outputs_per_chunk * cpb);
+        ascii_header_set(hdr, "SUBBAND", "%d", gpu);
+        ipcbuf_mark_filled(sink->header_block, hsz);
     }
+    const bool have_sink = sink != nullptr;
 
     ObservationLoopState obs(h, kMaxTransferSep, kMaxTotalSep, cpb, cfg.n_ring_slots, debug);
 #if BEAM_DEBUG
     obs.set_n_pt_sources(n_pt_sources);
 #else
     dada.read_headers();
+    if (dada.get_block_size() != block_bytes) {      // the H2D copies read block_bytes out of every ring block
+        fprintf(stderr, "beam: ring blocks are %llu bytes, this array shape needs %zu (dada_db -b %zu)\n",
+                (unsigned long long)dada.get_block_size(), block_bytes, block_bytes);
+        return EXIT_FAILURE;
+    }
 #endif
     if (verbose) {
         std::cout << "Executing beamformer (B200 fused path)\n";
@@ -170,7 +195,7 @@ int main(int argc, char *argv[])
     }
 #if !BEAM_DEBUG
     std::cout << "Burning IN" << std::endl;
-    for (int i = 0; i < kBurnIn; i++) { dada.read(); if (dada.get_bytes_read() == 0) break; dada.close(); }
+    for (int i = 0; i < kBurnIn; i++) { if (!dada.read() || dada.get_bytes_read() == 0) { dada.close(); break; } dada.close(); }
     std::cout << "Done Burn in" << std::endl;
 #endif
 
@@ -187,10 +212,11 @@ int main(int argc, char *argv[])
         // ---- copy data to the GPU (beamformer.cu:378-440) ----
         if (obs.ready_for_transfer()) {
 #if !BEAM_DEBUG
-            if (dada.in_flight() + 1 < dada.ring_blocks()) {
+            dada.retire(h);
+            if (dada.in_flight() == 0) {            // PSRDADA: one open block per reader; the previous one is still being copied otherwise
                 if (verbose) std::cout << "READING FROM PSRDADA" << std::endl;
                 char *block = dada.read();
-                if (!dada.check_transfers_complete()) {
+                if (block && !dada.check_transfers_complete()) {
                     uint64_t ticket = 0;
                     CHK(dsabf_enqueue_h2d(h, obs.next_transfer_slot(), block, block_bytes, &ticket));
                     obs.transfer_enqueued(ticket);
@@ -200,8 +226,6 @@ int main(int argc, char *argv[])
                     obs.set_transfers_complete(true);
                     dada.close();
                 }
-            } else {
-                dada.retire(h);   // ring nearly exhausted: only retire finished copies
             }
 #else
             if (generator.need_to_generate_more(obs.blocks_transferred())) {
@@ -243,16 +267,19 @@ int main(int argc, char *argv[])
         }
         obs.check_analysis_events(verbose);
         while (have_sink && blocks_sunk < obs.blocks_analyzed()) {       // hand finished blocks to the next stage, in order
-            char *dst = sink.open_block_write();
+            uint64_t id = 0;
+            char *dst = ipcio_open_block_write(sink->data_block, &id);
+            if (!dst) { fprintf(stderr, "beam: could not open an output block\n"); return EXIT_FAILURE; }
             memcpy(dst, beam_out + (blocks_sunk % kOutBufs) * out_block_floats, sizeof(float) * out_block_floats);
-            sink.close_block_write(sizeof(float) * out_block_floats);
+            // always the ring's full block size: a short block would end the data (PSRDADA semantics)
+            ipcio_close_block_write(sink->data_block, ipcbuf_get_bufsz((ipcbuf_t *)sink->data_block));
             blocks_sunk++;
         }
 #if !BEAM_DEBUG
         dada.retire(h);
 #endif
     }
-    if (have_sink) { sink.mark_eod(); sink.disconnect(); }
+    if (have_sink) { dada_hdu_unlock_write(sink); dada_hdu_destroy(sink); multilog_close(sink_log); }   // raises end of data
 
     // ---- report (beamformer.cu:539-557) ----
     observation_time_ms += sw.stop_ms();

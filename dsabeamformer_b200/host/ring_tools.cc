@@ -1,8 +1,10 @@
-// ring_tools.cc -- `ringdb` and `junkdb`: create / destroy the shared-memory ring and feed it,
-// standing in for PSRDADA's dada_db and dada_junkdb as the reference's makefile uses them
+// ring_tools.cc -- `ringdb` and `junkdb`: create / destroy a PSRDADA ring and feed it, standing in for
+// PSRDADA's dada_db and dada_junkdb as the reference's makefile uses them
 // (/root/reference/makefile:28-33: `dada_db -k baab -n 25 -b 134217728 -l -p`,
 // `dada_junkdb -c 0 -z -k baab -r 4050 -t 25 config/correlator_header_dsaX.txt`).
-//   ringdb -k KEY [-n NBUFS] [-b BUFSZ] [-d]          create (or -d destroy) the ring
+// Written against the PSRDADA C API (ipcbuf_create / dada_hdu_* / ipcio_open_block_write ...): links with the
+// shim library here, with -lpsrdada where PSRDADA is installed.
+//   ringdb -k KEY [-n NBUFS] [-b BUFSZ] [-d]          create (or -d destroy) header ring (KEY+1) and data ring (KEY)
 //   junkdb -k KEY [-r MB_PER_S] [-t SECONDS] [-n BLOCKS] [-g] [header_file]
 //          writes blocks of fixed-seed pseudo-random bytes (splitmix64, seed 0xD5A; every byte value
 //          is legal input) at the requested rate; -r 0 = as fast as possible; -n caps the block count;
@@ -13,10 +15,13 @@
 #include <fstream>
 #include <thread>
 #include <vector>
+#include <unistd.h>
 
-#include "dada_ring.hh"
-
-using namespace beam;
+#include "dada_def.h"
+#include "dada_hdu.h"
+#include "ipcbuf.h"
+#include "ipcio.h"
+#include "multilog.h"
 
 static uint64_t splitmix64(uint64_t &s)
 {
@@ -29,7 +34,7 @@ static uint64_t splitmix64(uint64_t &s)
 int main(int argc, char **argv)
 {
     const bool is_junk = strstr(argv[0], "junkdb") != nullptr;
-    unsigned key = 0xdada;
+    unsigned key = DADA_DEFAULT_BLOCK_KEY;
     uint64_t nbufs = 25, bufsz = 134217728;
     double rate = 4050, secs = 25;
     long max_blocks = -1;
@@ -48,18 +53,39 @@ int main(int argc, char **argv)
         }
     }
     if (!is_junk) {
-        if (destroy) { DadaRing::destroy(key); printf("destroyed ring %x\n", key); return 0; }
-        if (!DadaRing::create(key, nbufs, bufsz)) { fprintf(stderr, "ringdb: could not create ring %x\n", key); return 1; }
+        ipcbuf_t header = IPCBUF_INIT;
+        ipcio_t data = IPCIO_INIT;
+        if (destroy) {
+            int rc = 0;
+            if (ipcio_connect(&data, (key_t)key) == 0) ipcio_destroy(&data); else rc = 1;
+            if (ipcbuf_connect(&header, (key_t)(key + 1)) == 0) ipcbuf_destroy(&header); else rc = 1;
+            printf("destroyed ring %x\n", key);
+            return rc;
+        }
+        if (ipcbuf_create(&header, (key_t)(key + 1), 8, DADA_DEFAULT_HEADER_SIZE, 1) < 0 || ipcio_create(&data, (key_t)key, nbufs, bufsz, 1) < 0) {
+            fprintf(stderr, "ringdb: could not create ring %x\n", key);
+            return 1;
+        }
         printf("created ring %x: %llu blocks of %llu bytes\n", key, (unsigned long long)nbufs, (unsigned long long)bufsz);
+        ipcbuf_disconnect(&header);
+        ipcio_disconnect(&data);
         return 0;
     }
-    DadaRing ring;
-    if (!ring.connect(key)) { fprintf(stderr, "junkdb: could not connect to ring %x\n", key); return 1; }
-    std::vector<char> header(4096, 0);
-    if (optind < argc) { std::ifstream f(argv[optind]); f.read(header.data(), 4096); }
-    ring.write_header(header.data(), header.size());
+    multilog_t *log = multilog_open("junkdb", 0);
+    multilog_add(log, stderr);
+    dada_hdu_t *hdu = dada_hdu_create(log);
+    dada_hdu_set_key(hdu, (key_t)key);
+    if (dada_hdu_connect(hdu) < 0 || dada_hdu_lock_write(hdu) < 0) { fprintf(stderr, "junkdb: could not connect to ring %x\n", key); return 1; }
+    {
+        const uint64_t hsz = ipcbuf_get_bufsz(hdu->header_block);
+        char *hb = ipcbuf_get_next_write(hdu->header_block);
+        memset(hb, 0, hsz);
+        if (optind < argc) { std::ifstream f(argv[optind]); f.read(hb, (std::streamsize)hsz - 1); }
+        ipcbuf_mark_filled(hdu->header_block, hsz);
+    }
+    const uint64_t block = ipcbuf_get_bufsz((ipcbuf_t *)hdu->data_block);
     // one block of junk, generated once; each written block is a rotation of it
-    std::vector<char> junk(ring.bufsz());
+    std::vector<char> junk(block);
     uint64_t seed = 0xD5A;
     if (constant) memset(junk.data(), 0x70, junk.size());
     else for (size_t i = 0; i + 8 <= junk.size(); i += 8) { uint64_t v = splitmix64(seed); memcpy(&junk[i], &v, 8); }
@@ -69,19 +95,23 @@ int main(int argc, char **argv)
         const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if ((max_blocks >= 0 && blocks >= max_blocks) || (max_blocks < 0 && el >= secs)) break;
         if (rate > 0) {
-            const double due = (double)(blocks + 1) * ring.bufsz() / (rate * 1e6);
+            const double due = (double)(blocks + 1) * block / (rate * 1e6);
             if (due > el) std::this_thread::sleep_for(std::chrono::duration<double>(due - el));
         }
-        char *b = ring.open_block_write();
+        uint64_t id = 0;
+        char *b = ipcio_open_block_write(hdu->data_block, &id);
+        if (!b) { fprintf(stderr, "junkdb: could not open a block for writing\n"); return 1; }
         const size_t rot = (size_t)(blocks % 16) * 4096;
         memcpy(b, junk.data() + rot, junk.size() - rot);
         memcpy(b + junk.size() - rot, junk.data(), rot);
-        ring.close_block_write(ring.bufsz());
+        ipcio_close_block_write(hdu->data_block, block);
         blocks++;
     }
-    ring.mark_eod();
+    dada_hdu_unlock_write(hdu);          // closes the data block for writing: raises end of data
+    dada_hdu_destroy(hdu);
+    multilog_close(log);
     const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    printf("junkdb: wrote %ld blocks (%.1f MB) in %.2f s = %.1f MB/s\n", blocks, blocks * (double)ring.bufsz() / 1e6, el,
-           blocks * (double)ring.bufsz() / 1e6 / el);
+    printf("junkdb: wrote %ld blocks (%.1f MB) in %.2f s = %.1f MB/s\n", blocks, blocks * (double)block / 1e6, el,
+           blocks * (double)block / 1e6 / el);
     return 0;
 }

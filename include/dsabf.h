@@ -131,7 +131,7 @@ int dsabf_debug_voltages_host(dsabf_handle *h, const void *packed, int n_chunks,
  * d_power: [n_t][n_chan][n_beams] float in HBM; h_delay: [n_dm][n_chan] int32 >= 0
  * (host); d_out: [n_dm][n_t_out][n_beams] float in HBM:
  *   out[d][t][b] = sum_f power[t + delay[d][f]][f][b]   (terms with t+delay >= n_t dropped)
- * dsabf_dedisperse_device is stream-ordered (returns after enqueueing; h_delay may be reused at once);
+ * dsabf_dedisperse_device is stream-ordered (returns after enqueueing; h_delay is read by a stream-ordered copy: pageable memory may be reused at once, pinned memory only after the stream reaches this call);
  * stream NULL = the handle's compute stream, which dsabf_sync() drains. */
 int dsabf_dedisperse_device(dsabf_handle *h, const float *d_power, int n_t, int n_chan, int n_beams,
                             const int32_t *h_delay, int n_dm, int n_t_out, float *d_out, void *stream);

@@ -38,23 +38,50 @@ def test_usage_text_lists_reference_options():
         assert opt in out.stdout
 
 
-def test_ring_tools_roundtrip(tmp_path):
-    """ringdb + junkdb (stand-ins for dada_db / dada_junkdb): blocks arrive in order, full size, then EOD."""
-    reader = tmp_path / "reader.cc"
-    reader.write_text('''
-#include "dada_ring.hh"
+_READER_SRC = r"""
+// reads a ring through the PSRDADA API (host/psrdada_compat + libpsrdada_shim.a), like the reference's dada_handler
+#include "dada_hdu.h"
 #include <cstdio>
 int main(int argc, char** argv) {
-    unsigned key; sscanf(argv[1], "%x", &key);
-    beam::DadaRing r; if (!r.connect(key)) return 2;
-    uint64_t hs; r.read_header(&hs);
-    uint64_t n = 0, bytes, id; unsigned long long sum = 0;
-    for (;;) { char* b = r.open_block_read(&bytes, &id); if (bytes == 0) break; if (id != n) return 3;
-        for (uint64_t i = 0; i < bytes; i += 4096) sum += (unsigned char)b[i]; n++; r.close_block_read(); }
-    printf("blocks %llu bufsz %llu sum %llu\\n", (unsigned long long)n, (unsigned long long)r.bufsz(), sum); return 0; }
-''')
-    exe = tmp_path / "reader"
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "dsabeamformer_b200", "host"), str(reader), "-o", str(exe), "-lrt"])
+    unsigned key; sscanf(argv[1], "%%x", &key);
+    multilog_t* log = multilog_open("reader", 0);
+    dada_hdu_t* h = dada_hdu_create(log);
+    dada_hdu_set_key(h, (key_t)key);
+    if (dada_hdu_connect(h) < 0 || dada_hdu_lock_read(h) < 0) return 2;
+    uint64_t hs = 0; char* hdr = ipcbuf_get_next_read(h->header_block, &hs);
+    if (!hdr) return 4;
+    printf("header: %%.200s\n", hdr);
+    ipcbuf_mark_cleared(h->header_block);
+    uint64_t n = 0, bytes = 0, id = 0; unsigned long long sum = 0;
+    for (;;) {
+        char* b = ipcio_open_block_read(h->data_block, &bytes, &id);
+        if (!b) break;
+        if (bytes == 0) { ipcio_close_block_read(h->data_block, 0); break; }
+        if (id != n) return 3;
+        if (ipcio_open_block_read(h->data_block, &bytes, &id) != 0) return 5;     // PSRDADA: one open block per reader
+        %s
+        n++; ipcio_close_block_read(h->data_block, bytes);
+    }
+    printf("blocks %%llu bufsz %%llu sum %%llu\n", (unsigned long long)n, (unsigned long long)ipcbuf_get_bufsz((ipcbuf_t*)h->data_block), sum);
+    dada_hdu_unlock_read(h); dada_hdu_destroy(h); return 0; }
+"""
+
+
+def _build_ring_reader(tmp_path, name, per_block):
+    host = os.path.join(ROOT, "dsabeamformer_b200", "host")
+    src = tmp_path / (name + ".cc")
+    src.write_text(_READER_SRC % per_block)
+    exe = tmp_path / name
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(host, "psrdada_compat"), str(src), "-o", str(exe),
+                           os.path.join(host, "libpsrdada_shim.a"), "-lrt", "-lpthread"])
+    return exe
+
+
+def test_ring_tools_roundtrip(tmp_path):
+    """ringdb + junkdb (stand-ins for dada_db / dada_junkdb): blocks arrive in order, full size, then EOD."""
+    exe = _build_ring_reader(tmp_path, "reader", """
+        for (uint64_t i = 0; i < bytes; i += 4096) sum += (unsigned char)b[i];
+""")
     key = "%x" % (0xb000 + os.getpid() % 4096)
     subprocess.check_call([_need("ringdb"), "-k", key, "-n", "4", "-b", "1048576"])
     try:
@@ -150,6 +177,19 @@ def test_debug_program_matches_oracle_and_reference_binary(oracle, config_dir, t
         assert np.allclose(ours, theirs, rtol=2e-5)
         m = re.search(r"Time per data chunk: ([0-9.e+-]+)", rr.stdout)
         print("reference (sm_100 rebuild) time per data chunk [ms]:", m.group(1) if m else "?")
+        # The reference's OWN main() with the INTEGRATION.md drop-in applied (oracle/_ref/beam_ref_dsabf: its option
+        # parsing, generator, loop state, H2D ring, streams, gemv and data.py writer; expand + cuBLAS GEMM + detect replaced
+        # by dsabf_beamform_device on the same stream): same file, to the 6 digits it holds.
+        patched = os.path.join(ROOT, "oracle", "_ref", "beam_ref_dsabf")
+        if os.path.exists(patched):
+            pw = tmp_path / "patched"; (pw / "bin").mkdir(parents=True)
+            pr = subprocess.run([patched, "-p", cfg[0], "-d", cfg[1], "-s", cfg[2]], cwd=pw, capture_output=True, text=True, timeout=900)
+            assert pr.returncode == 0, pr.stdout[-1500:] + pr.stderr[-1500:]
+            mine = _load_data_py(pw / "bin" / "data.py")
+            assert mine.shape == theirs.shape and np.allclose(mine, theirs, rtol=2e-5)
+            assert np.allclose(mine, ours, rtol=2e-6)          # same kernel as bin/beam_debug, chunk by chunk instead of block by block
+            m = re.search(r"Time per data chunk: ([0-9.e+-]+)", pr.stdout)
+            print("reference main() + libdsabf time per data chunk [ms]:", m.group(1) if m else "?")
 
 
 @pytest.mark.gpu
@@ -194,6 +234,29 @@ def test_observation_program_streams_from_ring(config_dir):
         subprocess.call([_need("ringdb"), "-d", "-k", key])
 
 
+@pytest.mark.gpu
+def test_reference_observation_program_reads_our_ring(config_dir):
+    """Link- and run-compatibility of the PSRDADA shim: the reference's own observation build (src/beamformer.cu with
+    its dada_handler.hh, compiled unmodified against host/psrdada_compat + libpsrdada_shim by oracle/Makefile) attaches
+    to a ring made by bin/ringdb, pins it, burns in 25 blocks, consumes the data blocks bin/junkdb writes and stops at
+    the end-of-data block -- the same ring, header and blocks bin/beam reads."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "beam_ref_obs")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/beam_ref_obs not built (needs /root/reference at build time)")
+    key = "%x" % (0xa000 + os.getpid() % 4096)
+    subprocess.check_call([_need("ringdb"), "-k", key, "-n", "8", "-b", "134217728"])
+    try:
+        w = subprocess.Popen([_need("junkdb"), "-k", key, "-r", "0", "-n", "29", os.path.join(config_dir, "correlator_header_dsaX.txt")],
+                             stdout=subprocess.PIPE, text=True)
+        r = subprocess.run([exe, "-k", key, "-c", "-1", "-g", "0"], capture_output=True, text=True, timeout=600)
+        wout, _ = w.communicate(timeout=60)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "block size is: 134217728" in r.stdout and "Done Burn in" in r.stdout and "Freed CPU memory" in r.stdout
+        assert "wrote 29 blocks" in wout              # the writer only gets there if the reader released every block
+    finally:
+        subprocess.call([_need("ringdb"), "-d", "-k", key])
+
+
 def _splitmix64_block(n_bytes, seed=0xD5A):
     """the junk block of bin/junkdb (ring_tools.cc): splitmix64 stream, little-endian, vectorised"""
     with np.errstate(over="ignore"):
@@ -210,22 +273,10 @@ def test_observation_program_output_sink(bf, oracle, config_dir, tmp_path):
     """with DSABF_OUT_KEY bin/beam appends every finished block of power (float [time][chan][beam],
     64 MiB) to an output ring.  Three data blocks after the burn-in; the blocks read back must equal what the library
     computes for the same ring input (junkdb's splitmix64 block, rotated by (block % 16) * 4096 bytes)."""
-    reader = tmp_path / "dump.cc"
-    reader.write_text('''
-#include "dada_ring.hh"
-#include <cstdio>
-int main(int argc, char** argv) {
-    unsigned key; sscanf(argv[1], "%x", &key);
-    beam::DadaRing r; if (!r.connect(key)) return 2;
-    uint64_t hs; const char* h = r.read_header(&hs); printf("header: %.120s\\n", h);
-    uint64_t n = 0, bytes, id;
-    for (;;) { char* b = r.open_block_read(&bytes, &id); if (bytes == 0) break;
-        char name[256]; snprintf(name, sizeof name, "%s/block%llu.bin", argv[2], (unsigned long long)n);
-        FILE* f = fopen(name, "wb"); fwrite(b, 1, bytes, f); fclose(f); n++; r.close_block_read(); }
-    printf("blocks %llu\\n", (unsigned long long)n); return 0; }
-''')
-    exe = tmp_path / "dump"
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "dsabeamformer_b200", "host"), str(reader), "-o", str(exe), "-lrt"])
+    exe = _build_ring_reader(tmp_path, "dump", """
+        { char name[256]; snprintf(name, sizeof name, "%s/block%llu.bin", argv[2], (unsigned long long)n);
+          FILE* f = fopen(name, "wb"); fwrite(b, 1, bytes, f); fclose(f); }
+""")
     key_in, key_out = "%x" % (0xd000 + os.getpid() % 4096), "%x" % (0xe000 + os.getpid() % 4096)
     subprocess.check_call([_need("ringdb"), "-k", key_in, "-n", "8", "-b", "134217728"])
     subprocess.check_call([_need("ringdb"), "-k", key_out, "-n", "4", "-b", "67108864"])
@@ -239,17 +290,24 @@ int main(int argc, char** argv) {
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         d = subprocess.run([str(exe), key_out, str(tmp_path)], capture_output=True, text=True, timeout=120)
         assert d.returncode == 0 and "blocks 3" in d.stdout, d.stdout + d.stderr
-        assert "ORDER TFB" in d.stdout and "NBEAM 256" in d.stdout and "SUBBAND 2" in d.stdout
+        hdr = dict(l.split(None, 1) for l in d.stdout.splitlines() if len(l.split(None, 1)) == 2)
+        assert hdr.get("ORDER") == "TFB" and hdr.get("NBEAM") == "256" and hdr.get("SUBBAND") == "2" and hdr.get("NTIME") == "256", d.stdout
     finally:
         subprocess.call([_need("ringdb"), "-d", "-k", key_in])
         subprocess.call([_need("ringdb"), "-d", "-k", key_out])
     junk = _splitmix64_block(134217728)
     pos = oracle.read_positions(pfile); dirs = oracle.read_directions(dfile, 256)
     B = bf.Beamformer(debug=False)
-    B.set_weights(bf.compute_weights(pos, dirs, 2))
+    w = bf.compute_weights(pos, dirs, 2)
+    B.set_weights(w)
     for i, blk in ((0, 25), (2, 27)):                      # first and last data block (ring blocks 25 and 27 after the burn-in)
         packed = np.roll(junk, -((blk % 16) * 4096)).reshape(32, 256, 256, 64)
         got = np.fromfile(tmp_path / ("block%d.bin" % i), dtype=np.float32).reshape(256, 256, 256)
         assert np.array_equal(got, B.beamform(packed)), i
+        # and against the oracle (the reference's float detect_sum on exact int32 voltages) for two chunks of the block
+        for c in (0, 31):
+            ref = oracle.detect_ref_float(oracle.beamform(packed[c], w), 32)
+            rel = np.abs(got[c * 8:(c + 1) * 8] - ref) / np.maximum(ref, 1e-30)
+            assert rel.max() <= 1e-6, (i, c, rel.max())
     B.close()
 

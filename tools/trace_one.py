@@ -13,7 +13,7 @@ for _ in range(2):
 assert rc == 0
 t = tr.reshape(128, 16)
 t0 = t[8, 0]
-print("stage  mma:wait_start acquired issued | epi0: wait_start acquired loaded math_done | epi15: ... | unpack(item): start stg_ok b_empty_ok done")
+print("stage  mma:wait_start acquired issued | epi warp 8 (slice 0, first of its pair): loop_top loaded math_start math_issued | epi warp 23 (slice 3, second of its pair): ... | unpack(item): start stg_ok b_empty_ok done")
 for n in range(40, 72):
     r = t[n] - t0
     it = n // 4

@@ -9,7 +9,7 @@
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
-enum Op { FFMA2_DENORM, FFMA_DENORM, I2FP, IADD3, IMAD, FADD, FADD2, FFMA, FFMA2, LOP3, IMADWIDE, MIX_I2FP_FFMA2, MIX_IMAD_FADD2_FFMA2, MIX_HALF };
+enum Op { I2F_XU, I2F_F64, DFMA_OP, WIDE_CHAIN, MIX_XU3, MIX_XU4, MIX_XU3_WIDE2, MIX_F64, FFMA2_DENORM, FFMA_DENORM, I2FP, IADD3, IMAD, FADD, FADD2, FFMA, FFMA2, LOP3, IMADWIDE, MIX_I2FP_FFMA2, MIX_IMAD_FADD2_FFMA2, MIX_HALF };
 
 template <int OP>
 __global__ void __launch_bounds__(1024, 1) k(int iters, const int *in, int *out)
@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(1024, 1) k(int iters, const int *in, int *out)
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             if (OP == I2FP) asm volatile("cvt.rn.f32.s32 %0, %0;" : "+r"(r[j]));
-            if (OP == IADD3) asm volatile("add.s32 %0, %0, 0x4B400000;" : "+r"(r[j]));
+            if (OP == IADD3) asm volatile("add.s32 %0, %0, %1;" : "+r"(r[j]) : "r"(r[(j + 1) & 15]));
+            if (OP == I2F_XU) asm volatile("cvt.rp.f32.s32 %0, %0;" : "+r"(r[j]));
             if (OP == IMAD) asm volatile("mad.lo.s32 %0, %0, 3, 0x4B400000;" : "+r"(r[j]));
             if (OP == FADD) asm volatile("add.rn.f32 %0, %0, 0fCB400000;" : "+r"(r[j]));
             if (OP == FFMA) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+r"(r[j]));
@@ -43,6 +44,39 @@ __global__ void __launch_bounds__(1024, 1) k(int iters, const int *in, int *out)
             if (OP == FFMA2) asm volatile("fma.rn.f32x2 %0, %0, %0, %0;" : "+l"(q[j]));
             if (OP == FFMA2_DENORM) {   // operands stay denormal: x = x * 1.0 + 0 with x = small integer bit pattern
                 asm volatile("{.reg .b64 o, z; mov.b64 o, 0x3F8000003F800000; mov.b64 z, 0; fma.rn.f32x2 %0, %0, o, z;}" : "+l"(q[j]));
+            }
+            if (OP == I2F_F64) asm volatile("cvt.rn.f64.s32 %0, %1;" : "=l"(q[j]) : "r"((unsigned)q[j]));
+            if (OP == DFMA_OP) asm volatile("fma.rn.f64 %0, %0, %0, %0;" : "+l"(q[j]));
+            if (OP == WIDE_CHAIN) {           // two dependent 64-bit accumulates per accumulator, like the exact epilogue
+                asm volatile("mad.wide.s32 %0, %1, %1, %0;" : "+l"(q[j]) : "r"(r[2 * j]));
+                asm volatile("mad.wide.s32 %0, %1, %1, %0;" : "+l"(q[j]) : "r"(r[2 * j + 1]));
+            }
+            if (OP == MIX_XU3 || OP == MIX_XU4 || OP == MIX_XU3_WIDE2) {   // 16 elements: some converted on the XU pipe (I2F.RP), rest I2FP
+                const int nxu = OP == MIX_XU4 ? 4 : 3;
+                const bool wide = OP == MIX_XU3_WIDE2 && j == 7;           // one pair of 8 squared as integers
+                if (wide) {
+                    asm volatile("mad.wide.s32 %0, %1, %1, %0;" : "+l"(q[j]) : "r"(r[2 * j]));
+                    asm volatile("mad.wide.s32 %0, %1, %1, %0;" : "+l"(q[j]) : "r"(r[2 * j + 1]));
+                } else {
+                    if (j < nxu) asm volatile("cvt.rp.f32.s32 %0, %0;" : "+r"(r[2 * j]));
+                    else         asm volatile("cvt.rn.f32.s32 %0, %0;" : "+r"(r[2 * j]));
+                    asm volatile("cvt.rn.f32.s32 %0, %0;" : "+r"(r[2 * j + 1]));
+                    asm volatile("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(q[j]) : "r"(r[2 * j]), "r"(r[2 * j + 1]));
+                }
+            }
+            if (OP == MIX_F64) {              // 16 elements: 4 through I2F.F64 + DFMA, 12 through I2FP + FFMA2
+                if (j < 2) {
+                    unsigned long long d0, d1;
+                    asm volatile("cvt.rn.f64.s32 %0, %1;" : "=l"(d0) : "r"(r[2 * j]));
+                    asm volatile("cvt.rn.f64.s32 %0, %1;" : "=l"(d1) : "r"(r[2 * j + 1]));
+                    asm volatile("fma.rn.f64 %0, %1, %1, %0;" : "+l"(q[j]) : "l"(d0));
+                    asm volatile("fma.rn.f64 %0, %1, %1, %0;" : "+l"(q[j]) : "l"(d1));
+                    r[2 * j] ^= (unsigned)q[j]; r[2 * j + 1] += i;
+                } else {
+                    asm volatile("cvt.rn.f32.s32 %0, %0;" : "+r"(r[2 * j]));
+                    asm volatile("cvt.rn.f32.s32 %0, %0;" : "+r"(r[2 * j + 1]));
+                    asm volatile("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(q[j]) : "r"(r[2 * j]), "r"(r[2 * j + 1]));
+                }
             }
             if (OP == IMADWIDE) asm volatile("mad.wide.s32 %0, %1, %1, %0;" : "+l"(q[j]) : "r"(r[j]));
             if (OP == MIX_I2FP_FFMA2) {      // the current epilogue: 2 I2FP + 1 FFMA2 per 2 elements
@@ -112,6 +146,14 @@ int main()
     int h[1024]; for (int i = 0; i < 1024; i++) h[i] = (i * 7919) % 4001 - 2000;
     CK(cudaMemcpy(in, h, 4096, cudaMemcpyHostToDevice));
     printf("device %s, %d SMs, max clock %d MHz (rates assume the max clock)\n", prop.name, sms, clk_khz / 1000);
+    run<I2F_XU>("I2F.RP (XU pipe)", 16, 0, sms, clk_khz, in, out);
+    run<I2F_F64>("I2F.F64.S32", 8, 0, sms, clk_khz, in, out);
+    run<DFMA_OP>("DFMA", 8, 0, sms, clk_khz, in, out);
+    run<WIDE_CHAIN>("IMAD.WIDE chain x2", 16, 16, sms, clk_khz, in, out);
+    run<MIX_XU3>("3 I2F.RP+13 I2FP+8 FFMA2", 24, 16, sms, clk_khz, in, out);
+    run<MIX_XU4>("4 I2F.RP+12 I2FP+8 FFMA2", 24, 16, sms, clk_khz, in, out);
+    run<MIX_XU3_WIDE2>("3 XU+11 I2FP+7 FFMA2+2 WIDE", 23, 16, sms, clk_khz, in, out);
+    run<MIX_F64>("4 F64+12 I2FP+6 FFMA2", 26, 16, sms, clk_khz, in, out);
     run<FFMA_DENORM>("FFMA denormal operand", 16, 0, sms, clk_khz, in, out);
     run<FFMA2_DENORM>("FFMA2 denormal operand", 8, 0, sms, clk_khz, in, out);
     run<I2FP>("I2FP.F32.S32", 16, 0, sms, clk_khz, in, out);
