@@ -78,6 +78,10 @@ def lib():
     L.dsabf_transpose_pull_device.argtypes = [vp, vp, i, i, i, i, i, vp, vp]
     L.dsabf_dedisperse_single_peers_device.argtypes = [vp, vp, i, i, i, i, i, vp, i, vp, vp]
     L.dsabf_dedisperse_host.argtypes = [vp, vp, i, i, i, vp, i, i, vp]
+    L.dsabf_generate_test_data_device.argtypes = [vp, vp, vp, i, i, i, vp, vp]
+    L.dsabf_generate_test_data_host.argtypes = [vp, vp, vp, i, i, i, vp]
+    L.dsabf_dm_trials.argtypes = [ctypes.c_double, i, vp, i]
+    L.dsabf_dm_delays.argtypes = [vp, i, vp, i, vp]
     L.dsabf_kernel_launches.argtypes = [vp]; L.dsabf_kernel_launches.restype = ctypes.c_uint64
     L.dsabf_fused_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i), i]
     L.dsabf_enable_kernel_timing.argtypes = [vp, i]
@@ -112,6 +116,25 @@ def compute_weights(pos, dirs, gpu=0, n_chan=256):
     w = np.empty((n_chan, pos.shape[0], dirs.shape[0], 2), dtype=np.int8)
     _chk(lib().dsabf_compute_weights(_ptr(pos), _ptr(dirs), pos.shape[0], dirs.shape[0], n_chan, gpu, _ptr(w)))
     return w
+
+
+def dm_trials(dm_max=2000.0, n_chan_total=2048):
+    """DM trial list of sandbox/Dispersion Theory.ipynb cells 1-2 (1627 trials to DM 2000 at 2048 channels)."""
+    n = lib().dsabf_dm_trials(dm_max, n_chan_total, None, 0)
+    if n < 0:
+        raise DsabfError(n, lib().dsabf_last_error_string().decode())
+    dms = np.empty(n, dtype=np.float64)
+    lib().dsabf_dm_trials(dm_max, n_chan_total, _ptr(dms), n)
+    return dms
+
+
+def dm_delays(dms, freq_ghz):
+    """int32 [n_dm][n_chan] delays in output samples (cell 5 of the same notebook)."""
+    dms = np.ascontiguousarray(dms, dtype=np.float64)
+    freq_ghz = np.ascontiguousarray(freq_ghz, dtype=np.float64)
+    delay = np.empty((len(dms), len(freq_ghz)), dtype=np.int32)
+    _chk(lib().dsabf_dm_delays(_ptr(dms), len(dms), _ptr(freq_ghz), len(freq_ghz), _ptr(delay)))
+    return delay
 
 
 class Beamformer:
@@ -199,6 +222,22 @@ class Beamformer:
     def beamform_device(self, d_packed_ptr, n_chunks, d_out_ptr, stream=None):
         _chk(lib().dsabf_beamform_device(self._h, ctypes.c_void_p(d_packed_ptr), n_chunks, ctypes.c_void_p(d_out_ptr),
                                          ctypes.c_void_p(stream)))
+
+    # -- DEBUG-mode synthetic input (test_data_generator.hh:63-95) on the GPU --
+    def generate_test_data(self, pos, sources, batch=0, gpu=0):
+        """-> uint8 [1024][chan][col][ant]: batch `batch` of the point-source catalogue `sources` [n][2] (theta, phi)."""
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        sources = np.ascontiguousarray(sources, dtype=np.float32).reshape(-1, 2)
+        c = self.cfg
+        out = np.empty((1024, c.n_channels, self.cols_per_chunk, c.n_antennas), dtype=np.uint8)
+        _chk(lib().dsabf_generate_test_data_host(self._h, _ptr(pos), _ptr(sources), sources.shape[0], batch, gpu, _ptr(out)))
+        return out
+
+    def generate_test_data_device(self, pos, sources, d_dst_ptr, batch=0, gpu=0, stream=None):
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        sources = np.ascontiguousarray(sources, dtype=np.float32).reshape(-1, 2)
+        _chk(lib().dsabf_generate_test_data_device(self._h, _ptr(pos), _ptr(sources), sources.shape[0], batch, gpu, ctypes.c_void_p(d_dst_ptr),
+                                                   ctypes.c_void_p(stream)))
 
     # -- dedispersion --
     def dedisperse(self, power, delay, n_t_out):

@@ -300,6 +300,63 @@ cudaError_t launch_single(const Segments &seg, int n_t, int n_chan, int n_beams,
     return cudaGetLastError();
 }
 
+// A few trials (2..8): still one pass over the power.  Same streaming structure as the single-trial kernel -- thread =
+// (output time, 4 beams), 16-byte loads, channels in order -- with ND accumulators per thread.  The ND loads of a
+// channel hit rows a few samples apart; they are allowed to allocate in L1 (the threads of a block that cover
+// neighbouring times read the same rows for neighbouring trials) and otherwise come from L2, so HBM still sees every
+// row about once.  The staged kernel below needs ~8 trials per CTA to pay for its shared-memory staging and
+// barriers; under that it was latency-bound (1.3-1.6 TB/s of algorithmic bytes at 2-8 trials, r01).
+template <int ND, int UNROLL>
+__global__ void __launch_bounds__(256)
+dedisperse_few_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_beams, const int32_t *__restrict__ delay, int n_t_out,
+                      float *__restrict__ out)
+{
+    const int b4 = n_beams >> 2;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (long long)n_t_out * b4) return;
+    const int t = (int)(idx / b4), q = (int)(idx - (long long)t * b4);
+    const float4 *p4 = reinterpret_cast<const float4 *>(power) + q;
+    const size_t row4 = (size_t)b4;                                  // float4 per (time, channel) row
+    float4 acc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; d++) acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int f = 0;
+    for (; f + UNROLL <= n_chan; f += UNROLL) {
+        float4 v[UNROLL][ND];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+            for (int d = 0; d < ND; d++) {
+                const int tt = t + __ldg(delay + (size_t)d * n_chan + f + u);
+                v[u][d] = (tt < n_t) ? __ldg(p4 + ((size_t)tt * n_chan + f + u) * row4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+            for (int d = 0; d < ND; d++) { acc[d].x += v[u][d].x; acc[d].y += v[u][d].y; acc[d].z += v[u][d].z; acc[d].w += v[u][d].w; }
+    }
+    for (; f < n_chan; f++)
+#pragma unroll
+        for (int d = 0; d < ND; d++) {
+            const int tt = t + __ldg(delay + (size_t)d * n_chan + f);
+            if (tt < n_t) {
+                const float4 v = __ldg(p4 + ((size_t)tt * n_chan + f) * row4);
+                acc[d].x += v.x; acc[d].y += v.y; acc[d].z += v.z; acc[d].w += v.w;
+            }
+        }
+#pragma unroll
+    for (int d = 0; d < ND; d++) reinterpret_cast<float4 *>(out)[((size_t)d * n_t_out + t) * b4 + q] = acc[d];
+}
+
+template <int ND>
+cudaError_t launch_few(const float *d_power, int n_t, int n_chan, int n_beams, const int32_t *d_delay, int n_t_out, float *d_out, cudaStream_t stream)
+{
+    const long long n = (long long)n_t_out * (n_beams >> 2);
+    constexpr int UNROLL = ND <= 2 ? 4 : (ND <= 4 ? 2 : 1);          // 8 float4 loads in flight per thread
+    dedisperse_few_kernel<ND, UNROLL><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
+    return cudaGetLastError();
+}
+
 template <int STAGES, int TSPLIT>
 cudaError_t launch_stages(dim3 grid, const float *d_power, int n_t, int n_chan, int n_beams, const int32_t *d_delay, int n_dm, int n_t_out,
                           float *d_out, cudaStream_t stream)
@@ -323,6 +380,19 @@ cudaError_t launch_dedisperse(const float *d_power, int n_t, int n_chan, int n_b
         Segments seg{};
         seg.p[0] = d_power; seg.n_seg = 1; seg.c_seg = n_chan; seg.row_floats = n_beams; seg.col_off = 0;
         return launch_single(seg, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
+    }
+    // 2..8 trials on a problem large enough to fill the machine with one thread per (time, 4 beams): one streaming pass
+    if (n_dm >= 2 && n_dm <= 8 && (n_beams & 3) == 0 && ((uintptr_t)d_power & 15) == 0 && ((uintptr_t)d_out & 15) == 0 &&
+        (long long)n_t_out * (n_beams >> 2) >= 32768) {
+        switch (n_dm) {
+        case 2: return launch_few<2>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
+        case 3: return launch_few<3>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
+        case 4: return launch_few<4>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
+        case 5: return launch_few<5>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
+        case 6: return launch_few<6>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
+        case 7: return launch_few<7>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
+        default: return launch_few<8>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
+        }
     }
     // fewer than 8 trials: the 8 warps of a CTA split the output times instead of idling (tsplit = 8, 4, 2 for 1, 2, <=4 trials)
     const int tsplit = n_dm >= 5 ? 1 : (n_dm >= 3 ? 2 : (n_dm == 2 ? 4 : 8));

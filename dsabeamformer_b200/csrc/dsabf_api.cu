@@ -63,6 +63,7 @@ struct dsabf_handle {
     uint8_t *d_wprep = nullptr;    // tensor-core layout
     int *d_bad = nullptr;
     long long *d_trace = nullptr;  // debug: clock64 trace buffer (dsabf_debug_trace)
+    float *d_gen_par = nullptr;    // parameters of the GPU test-data generator
     int32_t *d_delay = nullptr; size_t delay_cap = 0;            // dedispersion delay table (grown on demand)
     cudaEvent_t ev_delay = nullptr; bool delay_in_use = false;   // last kernel that read it
 
@@ -282,6 +283,7 @@ int dsabf_destroy(dsabf_handle *h)
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     cudaFree(h->d_ring); cudaFree(h->d_out); cudaFree(h->d_ded); cudaFree(h->d_w); cudaFree(h->d_wprep); cudaFree(h->d_bad);
     cudaFree(h->d_delay);
+    cudaFree(h->d_gen_par);
     if (h->ev_delay) cudaEventDestroy(h->ev_delay);
     cudaFree(h->d_tmp_in); cudaFree(h->d_tmp_out);
     delete h;
@@ -575,6 +577,88 @@ int dsabf_dedisperse_host(dsabf_handle *h, const float *power, int n_t, int n_ch
     cudaFree(d_o);
     if (rc) return rc;
     if (e != cudaSuccess) return fail((int)e, "dedisperse_host");
+    return 0;
+}
+
+// ---- DEBUG-mode synthetic input on the GPU (test_data_generator.hh:63-95) -----------------
+// The float library calls of the reference's host loop (sinf of the source angles; the channel frequency from the
+// *double* bandwidth macro and the integer sub-band offset gpu*2048/7, :72; the float wavelength, :74) are evaluated
+// here on the host, exactly as the CPU generator does, and only the per-sample arithmetic runs in the kernel.
+int dsabf_generate_test_data_device(dsabf_handle *h, const float *pos, const float *sources, int n_sources, int batch, int gpu, void *d_dst,
+                                    void *stream)
+{
+    if (!h || !pos || (n_sources > 0 && !sources) || !d_dst || batch < 0 || n_sources < 0) return fail(DSABF_E_INVALID, "bad argument");
+    if ((uintptr_t)d_dst & 15) return fail(DSABF_E_INVALID, "d_dst must be 16-byte aligned");
+    CK(cudaSetDevice(h->device));
+    const dsabf_config &c = h->cfg;
+    const int per_batch = 1024;                                  // N_SOURCES_PER_BATCH
+    const long first = (long)batch * per_batch;
+    const int n_valid = (int)(n_sources - first < 0 ? 0 : (n_sources - first > per_batch ? per_batch : n_sources - first));
+    std::vector<float> host((size_t)2 * c.n_antennas + 2 * per_batch + c.n_channels, 0.f);
+    float *pxy = host.data(), *ssin = pxy + 2 * c.n_antennas, *wl = ssin + 2 * per_batch;
+    for (int k = 0; k < c.n_antennas; k++) { pxy[2 * k] = pos[3 * k]; pxy[2 * k + 1] = pos[3 * k + 1]; }
+    for (int s = 0; s < n_valid; s++) { ssin[2 * s] = sinf(sources[2 * (first + s)]); ssin[2 * s + 1] = sinf(sources[2 * (first + s) + 1]); }
+    const double bw = (1.53 - 1.28) / 2048;
+    for (int i = 0; i < c.n_channels; i++) {
+        const float freq = (float)(1.53 - (0 + gpu * 2048 / (8 - 1) + i) * bw);
+        wl[i] = (float)(299792458.0 / (1E9 * (double)freq));
+    }
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->s_comp;
+    if (!h->d_gen_par) CK(cudaMalloc(&h->d_gen_par, sizeof(float) * (2 * 256 + 2 * per_batch + 65536)));
+    if (host.size() > (size_t)(2 * 256 + 2 * per_batch + 65536)) return fail(DSABF_E_INVALID, "more than 65536 channels");
+    CK(cudaStreamSynchronize(st));                               // the parameter block is reused: previous generator launch must be done
+    CK(cudaMemcpyAsync(h->d_gen_par, host.data(), sizeof(float) * host.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                               // `host` goes out of scope
+    CK(dsabf::launch_generate_test_data((uint8_t *)d_dst, h->d_gen_par, h->d_gen_par + 2 * c.n_antennas, h->d_gen_par + 2 * c.n_antennas + 2 * per_batch,
+                                        per_batch, n_valid, c.n_antennas, c.n_channels, h->cols_per_chunk, st));
+    h->launches++;
+    return 0;
+}
+
+int dsabf_generate_test_data_host(dsabf_handle *h, const float *pos, const float *sources, int n_sources, int batch, int gpu, void *dst)
+{
+    if (!h || !dst) return fail(DSABF_E_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    const size_t bytes = h->chunk_bytes * 1024;
+    int rc = ensure_tmp(h, bytes, 0);
+    if (rc) return rc;
+    rc = dsabf_generate_test_data_device(h, pos, sources, n_sources, batch, gpu, h->d_tmp_in, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(dst, h->d_tmp_in, bytes, cudaMemcpyDeviceToHost, h->s_comp));
+    CK(cudaStreamSynchronize(h->s_comp));
+    return 0;
+}
+
+// ---- dedispersion plan (host): DM trial list and delay table -------------------------
+// Trial spacing of sandbox/Dispersion Theory.ipynb cells 1-2: each next trial is the DM at which the smearing of a
+// pulse dedispersed at the previous trial has grown by the tolerance epsilon (channel width B MHz at nu GHz, intrinsic
+// width 40 us, sampling 131 us); 2048 channels to DM 2000 gives 1627 trials.
+int dsabf_dm_trials(double dm_max, int n_chan_total, double *dms, int capacity)
+{
+    if (n_chan_total < 1 || (capacity > 0 && !dms)) { fail(DSABF_E_INVALID, "bad argument"); return -1; }
+    const double eps2 = 1.25 * 1.25, nc2 = (double)n_chan_total * n_chan_total;
+    const double alpha = 1.0 / (16 + nc2), centre_ghz = (1.28 + 1.53) / 2, chan_mhz = (1.53 - 1.28) / n_chan_total * 1000;
+    const double width2_us = 40.0 * 40.0 + 0.0 * 0.0 + 131.0 * 131.0;
+    const double smear = centre_ghz * centre_ghz * centre_ghz / (8.3 * chan_mhz);
+    const double floor_term = alpha * width2_us * (eps2 - 1) * smear * smear;
+    int n = 0;
+    for (double dm = 0;; dm = nc2 * alpha * dm + 4 * sqrt(alpha * (eps2 - nc2 * alpha) * dm * dm + floor_term)) {
+        if (n < capacity) dms[n] = dm;
+        n++;
+        if (!(dm < dm_max)) break;
+    }
+    return n;
+}
+
+// Delay of channel f (centre freq_ghz[f]) relative to the top of the band, in output samples of 16 x 131 us
+// (cell 5 of the same notebook): int(4.15 DM (f^-2 - 1.53^-2) / (0.131 * 16)), truncated toward zero.
+int dsabf_dm_delays(const double *dms, int n_dm, const double *freq_ghz, int n_chan, int32_t *delay)
+{
+    if (!dms || !freq_ghz || !delay || n_dm < 1 || n_chan < 1) return fail(DSABF_E_INVALID, "bad argument");
+    const double top = 1.53, sample_ms = 0.131 * 16;
+    for (int d = 0; d < n_dm; d++)
+        for (int f = 0; f < n_chan; f++)
+            delay[(size_t)d * n_chan + f] = (int32_t)(4.15 * dms[d] * (-1.0 / (top * top) + 1.0 / (freq_ghz[f] * freq_ghz[f])) / sample_ms);
     return 0;
 }
 

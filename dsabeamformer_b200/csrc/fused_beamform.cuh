@@ -38,4 +38,8 @@ cudaError_t launch_transpose_pull(const float *const *peer_power, int world, int
 cudaError_t launch_dedisperse(const float *d_power, int n_t, int n_chan, int n_beams, const int32_t *d_delay, int n_dm,
                               int n_t_out, float *d_out, cudaStream_t stream);
 
+// test_data_gen.cu: the DEBUG-mode synthetic input on the GPU (test_data_generator.hh:63-95)
+cudaError_t launch_generate_test_data(uint8_t *d_dst, const float *d_pos_xy, const float *d_src_sin, const float *d_wavelength, int n_chunks,
+                                      int n_valid, int n_ant, int n_chan, int cols, cudaStream_t stream);
+
 }  // namespace dsabf

@@ -113,6 +113,7 @@ int main(int argc, char *argv[])
 
 #if BEAM_DEBUG
     TestDataGenerator generator(cfg);
+    generator.use_gpu(h);
     if (!source_file.empty()) generator.read_in_source_directions(source_file.c_str(), verbose);
     else std::cout << "Using BOGUS DATA " << std::endl;
     const int n_pt_sources = generator.n_pt_sources();

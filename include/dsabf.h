@@ -138,6 +138,24 @@ int dsabf_dedisperse_device(dsabf_handle *h, const float *d_power, int n_t, int 
 int dsabf_dedisperse_host(dsabf_handle *h, const float *power, int n_t, int n_chan, int n_beams,
                           const int32_t *delay, int n_dm, int n_t_out, float *out);
 
+/* ---- DEBUG-mode synthetic input, generated on the GPU (test_data_generator::generate_test_data,
+ * src/test_data_generator.hh:63-95): batch `batch` of 1024 chunks, one point source per chunk (sources
+ * [1024*batch, 1024*batch + 1024) of the n_sources given as host pairs (theta, phi) in radians; chunks past the last
+ * source are zero bytes), pos = host [n_antennas][3] metres, gpu = sub-band index (-g).  Same bytes as the CPU loop.
+ * _device writes 1024 * dsabf_chunk_bytes() bytes of device memory (16-byte aligned; stream NULL = compute stream);
+ * _host additionally copies them into dst (host, ideally pinned) and returns when they are there. */
+int dsabf_generate_test_data_device(dsabf_handle *h, const float *pos, const float *sources, int n_sources, int batch,
+                                    int gpu, void *d_dst, void *stream);
+int dsabf_generate_test_data_host(dsabf_handle *h, const float *pos, const float *sources, int n_sources, int batch,
+                                  int gpu, void *dst);
+
+/* Host side of the dedispersion stage: the DM trial list of sandbox/Dispersion Theory.ipynb cells 1-2 (2048 channels
+ * to DM 2000: 1627 trials) and the integer delay table of its cell 5 in output samples (16 x 131 us).
+ * dsabf_dm_trials returns the number of trials (also when it exceeds capacity; only the first `capacity` are
+ * written), -1 on a bad argument.  delay: [n_dm][n_chan], freq_ghz: channel centre frequencies. */
+int dsabf_dm_trials(double dm_max, int n_chan_total, double *dms, int capacity);
+int dsabf_dm_delays(const double *dms, int n_dm, const double *freq_ghz, int n_chan, int32_t *delay);
+
 /* ---- multi-GPU exchange in front of full-band dedispersion (the reference has none: each
  * `beam -g <k>` process sums only its own 256 channels, beamformer.cu:498-504) ----
  * peer_power[g]: device pointer, valid on THIS GPU, to GPU g's power [n_t][c_local][n_beams] (peer-mapped

@@ -66,3 +66,17 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cc", ".hh", ".h", ".cpp")) or f == "Makefile":
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in src.lower(), os.path.join(dirpath, f)
+
+
+def test_dm_plan_matches_oracle(oracle):
+    """dsabf_dm_trials / dsabf_dm_delays (product host code, no GPU needed) == the oracle's restatement of
+    sandbox/Dispersion Theory.ipynb cells 2 and 5: 1627 trials to DM 2000, identical integer delays over the band."""
+    import dsabeamformer_b200 as bf
+    dms = bf.dm_trials(2000.0, 2048)
+    ref = oracle.dm_trials(2000.0, 2048)
+    assert len(dms) == len(ref) == 1627 and np.array_equal(dms, ref)
+    assert len(bf.dm_trials(100.0, 840)) == len(oracle.dm_trials(100.0, 840))
+    freq = 1.28 + (1.53 - 1.28) / 2048 * np.arange(2048)               # the notebook's channel grid
+    d = bf.dm_delays(dms[::25], freq)
+    assert d.dtype == np.int32 and np.array_equal(d, oracle.dm_delays(dms[::25], freq))
+    assert d[0].max() == 0 and d[-1, 0] == int(4.15 * dms[::25][-1] * (1.28 ** -2 - 1.53 ** -2) / (0.131 * 16))

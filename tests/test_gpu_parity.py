@@ -346,3 +346,133 @@ def test_dedisperse_recovers_injected_pulse(bf, oracle):
     peak = np.unravel_index(np.argmax(ded[:, :, 5]), ded[:, :, 5].shape)
     assert peak == (true, 50)
     B.close()
+
+
+@pytest.mark.parametrize("case", ["linear_g0", "grid4096_g0", "grid3721_g3"])
+def test_gpu_generator_matches_reference_golden(bf, oracle, golden, config_dir, case):
+    """csrc/test_data_gen.cu (dsabf_generate_test_data_host) == the reference's compiled generator loop
+    (src/test_data_generator.hh:63-95): sha256 of every 256 MiB batch, tests/golden/ref_host_golden.json; the zero tail of
+    the last batch of the 3721-source catalogue included.  Timed against the oracle's OpenMP loop for the record."""
+    import hashlib
+    import time
+    g, _ = golden
+    e = g[case]
+    pos = oracle.read_positions(os.path.join(config_dir, e["positions"]))
+    src = oracle.read_directions(os.path.join(config_dir, e["sources"]))
+    B = bf.Beamformer(debug=True)
+    for b, sha in enumerate(e["data_sha256"]):
+        t0 = time.perf_counter()
+        data = B.generate_test_data(pos, src, batch=b, gpu=e["gpu"])
+        t_gpu = time.perf_counter() - t0
+        assert hashlib.sha256(data.tobytes()).hexdigest() == sha, (case, b)
+    t0 = time.perf_counter()
+    oracle.generate(pos, src, batch=0, gpu=e["gpu"])
+    print("%s: GPU generator %.3f s per batch incl. the copy to host; oracle CPU loop %.2f s" % (case, t_gpu, time.perf_counter() - t0))
+    B.close()
+
+
+def test_gpu_generator_device_feeds_the_kernel(bf, oracle, config_dir):
+    """generate straight into device memory and beamform from there (no host round trip): same power as from the
+    host-generated batch"""
+    import torch
+    pos = oracle.read_positions(os.path.join(config_dir, "grid_positions.txt"))
+    dirs = oracle.read_directions(os.path.join(config_dir, "grid_beam_directions.txt"), 256)
+    src = oracle.read_directions(os.path.join(config_dir, "grid_source_directions_4096.txt"))
+    B = bf.Beamformer(debug=True)
+    B.set_weights(bf.compute_weights(pos, dirs, 0))
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        d = torch.empty(1024 * B.chunk_bytes, dtype=torch.uint8, device="cuda")
+        out = torch.empty(64 * B.chunk_out_floats, dtype=torch.float32, device="cuda")
+        B.generate_test_data_device(pos, src, d.data_ptr(), batch=2, gpu=0, stream=st.cuda_stream)
+        B.beamform_device(d.data_ptr() + 100 * B.chunk_bytes, 64, out.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    host = oracle.generate(pos, src, batch=2)
+    assert np.array_equal(d.cpu().numpy(), host.reshape(-1))
+    assert np.array_equal(out.cpu().numpy().reshape(64 * 8, 256, 256), B.beamform(host[100:164]))
+    B.close()
+
+
+def test_dedisperse_full_band_unclamped_delays(bf, oracle):
+    """2048 channels over the whole band with the delays the trial list really has up to DM 2000 (725 samples between the
+    top and the bottom channel): the wide-window path of the staged kernel (csrc/dedisperse.cu, windows > 64 rows read
+    from global memory) next to the shared-memory path of the low-DM trials, and the single-trial kernel at the
+    largest DM.  VERDICT r01: parity was only shown with delays clamped to 60."""
+    rng = np.random.default_rng(21)
+    n_chan, n_beams = 2048, 32
+    freq = 1.28 + (1.53 - 1.28) / n_chan * np.arange(n_chan)
+    dms = bf.dm_trials(2000.0, 2048)
+    pick = np.array([0, 1, 2, 3, 40, 400, 800, 1200, 1500, 1600, 1625, 1626])
+    delay = bf.dm_delays(dms[pick], freq)
+    assert delay.max() >= 700                              # unclamped: DM 2000 spreads over > 700 output samples
+    n_t = int(delay.max()) + 48
+    power = rng.random((n_t, n_chan, n_beams), dtype=np.float32) * 50
+    B = bf.Beamformer(debug=True, n_channels=1)
+    got = B.dedisperse(power, delay, 48)
+    ref = oracle.dedisperse(power, delay, 48)
+    rel = np.abs(got - ref) / ref
+    assert rel.max() <= 5e-6, rel.max()                    # fp32 sums of 2048 positive terms in two orders
+    one = B.dedisperse(power, delay[-1:], 48)              # single-trial streaming kernel at the largest DM
+    assert (np.abs(one[0] - ref[-1]) / ref[-1]).max() <= 5e-6
+    for n in (2, 5, 8):                                    # the 2-, 5+- and 8-trial splits with wide windows
+        sub = np.ascontiguousarray(delay[-n:])
+        assert (np.abs(B.dedisperse(power, sub, 48) - ref[-n:]) / ref[-n:]).max() <= 5e-6, n
+    B.close()
+
+
+def test_two_handles_two_threads_one_process(bf, oracle):
+    """Handles are per GPU and per host thread: two handles (on two devices when the box has them, else both on
+    device 0) driven from two threads at once, shapes that need the > 48 KB dynamic shared-memory opt-in of all three
+    kernels (resident, streamed, dedispersion).  ADVICE r01: the opt-in used to be cached in a process-wide static."""
+    import threading
+    import torch
+    n_dev = torch.cuda.device_count()
+    rng = np.random.default_rng(3)
+    w_small = rng.integers(-127, 128, size=(3, 64, 256, 2), dtype=np.int8)
+    w_big = rng.integers(-127, 128, size=(2, 128, 512, 2), dtype=np.int8)
+    x_small = rng.integers(0, 256, size=(2, 3, 256, 64), dtype=np.uint8)
+    x_big = rng.integers(0, 256, size=(1, 2, 256, 128), dtype=np.uint8)
+    pw = rng.random((64, 24, 64), dtype=np.float32)
+    delay = np.minimum(np.arange(9)[:, None] * np.arange(24)[None, :] // 6, 20).astype(np.int32)
+    want = (oracle.power_int(oracle.beamform(x_small[1], w_small), 32), oracle.power_int(oracle.beamform(x_big[0], w_big), 32),
+            oracle.dedisperse(pw, delay, 40))
+    errors = []
+
+    def work(dev):
+        try:
+            for _ in range(3):
+                A = bf.Beamformer(debug=False, n_channels=3, device=dev, exact_power=1, power_scale=1.0)
+                A.set_weights(w_small)
+                assert np.array_equal(A.beamform(x_small)[8:], want[0].astype(np.float32))
+                Bg = bf.Beamformer(debug=False, n_channels=2, n_antennas=128, n_beams=512, device=dev, exact_power=1, power_scale=1.0)
+                Bg.set_weights(w_big)
+                assert np.array_equal(Bg.beamform(x_big), want[1].astype(np.float32))
+                assert np.allclose(A.dedisperse(pw, delay, 40), want[2], rtol=2e-6)
+                A.close(); Bg.close()
+        except Exception as ex:                    # noqa: BLE001 -- reported by the main thread
+            errors.append((dev, repr(ex)))
+
+    threads = [threading.Thread(target=work, args=(d,)) for d in ([0, 1] if n_dev >= 2 else [0, 0])]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
+@pytest.mark.parametrize("n_dm", [2, 3, 4, 5, 6, 7, 8])
+def test_dedisperse_few_trials_streaming(bf, oracle, n_dm):
+    """2..8 trials on a problem large enough for the one-pass streaming kernel (dedisperse_few_kernel: one thread per
+    (time, 4 beams), n_dm accumulators): ragged channel count (tail loop), rows past the end of the power dropped."""
+    rng = np.random.default_rng(40 + n_dm)
+    n_chan, n_beams, n_t_out = 67, 64, 2048
+    dms = bf.dm_trials(2000.0, 2048)[[0, 3, 200, 600, 900, 1200, 1500, 1626][:n_dm]]
+    freq = 1.53 - np.arange(n_chan) * (0.25 / n_chan)
+    delay = bf.dm_delays(dms, freq)
+    n_t = n_t_out + int(delay.max()) - 5                     # the last five output times of the largest DM run off the end
+    power = rng.random((n_t, n_chan, n_beams), dtype=np.float32) * 10
+    B = bf.Beamformer(debug=True, n_channels=1)
+    got = B.dedisperse(power, delay, n_t_out)
+    ref = oracle.dedisperse(power, delay, n_t_out)
+    assert np.allclose(got, ref, rtol=2e-6, atol=1e-4)
+    B.close()

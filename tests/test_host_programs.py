@@ -193,6 +193,45 @@ def test_debug_program_matches_oracle_and_reference_binary(oracle, config_dir, t
 
 
 @pytest.mark.gpu
+def test_debug_program_grid_4096_sources(oracle, config_dir, tmp_path):
+    """Config 2 end to end (BASELINE.json configs[1]): the 2-D grid array with 4096 source directions drives the
+    regenerate-in-place path four times (src/beamformer.cu:405-418, test_data_generator.hh:98-108): 4 generator batches
+    = 128 blocks.  bin/data.py [4096][256] against the oracle (sources from every batch) and against the reference's own
+    DEBUG binary on the same files; once more with the CPU generator (DSABF_CPU_GENERATOR=1): identical file."""
+    cfg = [os.path.join(config_dir, f) for f in ("grid_positions.txt", "grid_beam_directions.txt", "grid_source_directions_4096.txt")]
+    work = tmp_path / "ours"; (work / "bin").mkdir(parents=True)
+    r = subprocess.run([_need("beam_debug"), "-p", cfg[0], "-d", cfg[1], "-s", cfg[2]], cwd=work, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("Generating new source data") == 4 and "obs Complete" in r.stdout
+    m = re.search(r"Code produced outputs for (\d+) data chunks", r.stdout)
+    assert m and int(m.group(1)) == 4096 * 8
+    t_ours = float(re.search(r"Observation ran in ([0-9.e+-]+)", r.stdout).group(1))
+    ours = _load_data_py(work / "bin" / "data.py")
+    assert ours.shape == (4096, 256)
+    pos = oracle.read_positions(cfg[0]); dirs = oracle.read_directions(cfg[1], 256); src = oracle.read_directions(cfg[2])
+    w = oracle.weights(pos, dirs, 0)
+    for b in range(4):
+        data = oracle.generate(pos, src, batch=b)
+        for s in (0, 517, 1023):
+            ref = oracle.dm0(oracle.detect_ref_float(oracle.beamform(data[s], w), 2))
+            assert np.allclose(ours[1024 * b + s], ref, rtol=2e-5), (b, s)
+    cw = tmp_path / "cpu"; (cw / "bin").mkdir(parents=True)
+    rc = subprocess.run([_need("beam_debug"), "-p", cfg[0], "-d", cfg[1], "-s", cfg[2]], cwd=cw, capture_output=True, text=True, timeout=1800,
+                        env=dict(os.environ, DSABF_CPU_GENERATOR="1"))
+    assert rc.returncode == 0, rc.stdout[-2000:] + rc.stderr[-2000:]
+    assert (cw / "bin" / "data.py").read_bytes() == (work / "bin" / "data.py").read_bytes()
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "beam_ref")
+    if os.path.exists(ref_exe):
+        rw = tmp_path / "ref"; (rw / "bin").mkdir(parents=True)
+        rr = subprocess.run([ref_exe, "-p", cfg[0], "-d", cfg[1], "-s", cfg[2]], cwd=rw, capture_output=True, text=True, timeout=3000)
+        assert rr.returncode == 0, rr.stdout[-1500:] + rr.stderr[-1500:]
+        theirs = _load_data_py(rw / "bin" / "data.py")
+        assert theirs.shape == ours.shape and np.allclose(ours, theirs, rtol=2e-5)
+        t_ref = float(re.search(r"Observation ran in ([0-9.e+-]+)", rr.stdout).group(1))
+        print("config 2 (4096 grid sources): observation time ours %.1f ms, reference (sm_100 rebuild) %.1f ms" % (t_ours, t_ref))
+
+
+@pytest.mark.gpu
 def test_debug_program_scaled_array(oracle, config_dir, tmp_path):
     """BASELINE.json configs[3] through the drop-in program: 256 antennas x 2048 beams (16 channels of the band),
     64 seeded sources; bin/data.py [source][beam] against the oracle's float path."""

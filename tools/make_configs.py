@@ -4,15 +4,20 @@
 The reference ships its inputs as text files (format: SURVEY.md section 5.6;
 parsers at /root/reference/src/beamformer.hh:250-284 and
 src/test_data_generator.hh:43-60).  They are all formula-generated grids, so we
-regenerate them here instead of copying them; tests/test_configs.py checks, where
+regenerate them here instead of copying them; tests/test_oracle_golden.py
+(test_generated_configs_parse_like_reference) checks, where
 the reference is mounted, that every value parses to the *same float32* as the
 reference's file of the same name.
 
     positions : first token = count, then "x y z" per antenna, metres
     directions: first token = count, then "theta phi" per beam/source, radians
 
-random_positions.txt is our own fixed-seed draw (the reference's is an unseeded
-random draw and is not used by any named configuration).
+random_positions.txt is the one exception: the reference's file of that name is an
+unseeded random draw (sandbox notebook), cannot be regenerated and is not used by any
+named configuration, so ours is a fixed-seed draw of the same kind (64 antennas uniform in
++-250 m) under the same name -- NOT the same numbers.  The reference's own file is read by
+the same parser (`bin/beam -p <reference>/config/random_positions.txt`;
+tests/test_oracle_golden.py::test_reference_random_positions_parse).
 """
 import os
 import sys
