@@ -69,6 +69,19 @@ constexpr bool kEpiPingPong = DSABF_EPI_PP != 0;
 #define DSABF_ROLE_ORDER 0
 #endif
 constexpr bool kProducersOnTop = DSABF_ROLE_ORDER != 0;
+// kEpiProbe (-DDSABF_EPI_PROBE): the epilogue's wait for the next accumulator stage costs a ~90-clock mbarrier.try_wait round
+// trip even though the stage is practically always full already (ncu: 18 % of the epilogue warps' samples sit behind it).
+//   1  probe the NEXT stage's barrier between the two 32-column blocks of arithmetic; the answer is back by the loop top
+//   2  as 1, with hint-free probes (one SYNCS instruction instead of TRYWAIT + NANOSLEEP.SYNCS + PHASECHK)
+#ifndef DSABF_EPI_PROBE
+#define DSABF_EPI_PROBE 0
+#endif
+constexpr int kEpiProbe = DSABF_EPI_PROBE;
+#ifdef DSABF_BIAS_SKIP_MMA      // timing experiment only (wrong results): the FMA-pipe epilogue without the bias MMA
+constexpr bool kBiasSkipMma = true;
+#else
+constexpr bool kBiasSkipMma = false;
+#endif
 static_assert(kEpiWarp0 == 8 && kNumEpiWarps == 16 && kUnpackWarp0 == 4 && kNumUnpackWarps == 4, "role remap assumes this layout");
 
 
@@ -82,6 +95,9 @@ struct __align__(1024) Smem {
     uint64_t acc_full[2], acc_empty[2];
     uint64_t epi_go[kNumEpiWarps];       // arithmetic hand-over between the two epilogue warps of a pair (kEpiPingPong)
     uint32_t tmem_base;
+    // all-0xFF operand of the bias MMA (A: 128 rows, B: kBiasCols rows of one 128-byte swizzle row each; the content
+    // is constant, so the swizzle pattern does not matter and A and B share the bytes)
+    alignas(1024) uint8_t bias_ff[kBiasCols > 0 ? (kBiasCols > 128 ? kBiasCols : 128) * kRowBytes : 1024];
 };
 
 // MODE: 0 = fast fp32 power, 1 = exact int64 power (+ optional integer-power dump),
@@ -123,6 +139,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
         fence_mbar_init();
     }
     if (warp == 2) { tmem_alloc(&sm.tmem_base, kTmemCols); tmem_relinquish(); }
+    if (kBiasCols > 0 && !EXACT) {
+        for (uint32_t i = threadIdx.x; i < sizeof(sm.bias_ff) / 16; i += kThreads) reinterpret_cast<uint4 *>(sm.bias_ff)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -215,6 +235,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
 #pragma unroll
                     for (int k = 0; k < kRowBytes / 32; k++)   // K = 32 bytes per instruction; +32 B = +2 in the descriptor
                         mma_i8_ss(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0);
+                    if (kBiasCols > 0 && !EXACT && !kBiasSkipMma) {             // + 32 * 255 * 255 on columns [0, kBiasCols): see Acc<false>::add2b
+                        const uint64_t ffdesc = make_desc_k_sw128(sbase + (uint32_t)offsetof(Smem, bias_ff));
+                        mma_i8_ss(d, ffdesc, ffdesc, make_idesc_u8(128, kBiasCols > 0 ? kBiasCols : 64), 1);
+                    }
                     tc_commit(bar_acc_full + 8 * me);
                     if (kTrace && p.trace && blockIdx.x == 0 && acc_cnt < 128) p.trace[acc_cnt * 16 + 2] = clock64();
                     if (last_of_ch) { tc_commit(bar_a_empty + 8 * m); released |= 1u << m; }
@@ -286,13 +310,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
         ctx.lane_odd = lane & 1;
         const size_t tstride = (size_t)g.n_chan * p.n_beams;      // floats between consecutive output times
         ctx.pair_stride = 2 * tstride;
-        ctx.scale = p.scale;
+        const bool biased = kBiasCols > 0 && !EXACT && wc * kEpiCols < kBiasCols;     // warp-uniform: this slice converts on the FMA pipe
+        ctx.scale = biased ? p.scale * kBiasUnscale : p.scale;
         uint32_t acc_cnt = 0;
         int f = item_begin / g.n_tiles, t = item_begin - f * g.n_tiles - 1;   // advanced incrementally: no division per item
         const uint32_t n_acc_total = (uint32_t)(item_end - item_begin) * (uint32_t)mt;
         const bool pp_second = (wc & 2) != 0;
         const uint32_t bar_go_mine = bar_epi_go + 8 * ew, bar_go_partner = bar_epi_go + 8 * (ew ^ 8);
         uint32_t va[32], vb[32];
+        bool probed = false;        // kEpiProbe: the barrier of the tile about to be loaded was already seen complete
         // kEpiPipe (-DDSABF_EPI_PIPE): how far the TMEM loads of the next M-tile run ahead of this tile's arithmetic
         //   0  load, wait, square, store -- strictly in sequence
         //   1  the next tile's loads are put in flight before this tile's last shuffle + store
@@ -324,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 if (trc) p.trace[trb + 0] = clock64();
                 FSTAMP(0);
                 if (kEpiPipe == 0) {
-                    mbar_wait(bar_acc_full + 8 * as, (acc_cnt >> 1) & 1, 8);
+                    if (!(kEpiProbe > 0 && probed)) mbar_wait(bar_acc_full + 8 * as, (acc_cnt >> 1) & 1, 8);
                     tc_fence_after();
                     FSTAMP(1);
                     tmem_ld_2x32_wait(tbase_w + as * kAccCols, va, vb);
@@ -368,14 +394,19 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 ctx.pend = 0;
                 ctx.op = out_item;
                 ctx.pp = pp_item;
-                epi_block<G, EXACT, 0>(ctx, va);
+                if (biased) epi_block<G, EXACT, 0, true>(ctx, va); else epi_block<G, EXACT, 0>(ctx, va);
+                if (kEpiProbe > 0) {
+                    probed = false;
+                    if (has_next) probed = kEpiProbe == 2 ? mbar_try_wait_nohint(bar_acc_full + 8 * nas, ((acc_cnt + 1) >> 1) & 1)
+                                                          : mbar_try_wait(bar_acc_full + 8 * nas, ((acc_cnt + 1) >> 1) & 1);
+                }
                 FSTAMP(6);
                 if (kEpiPipe == 2 && has_next) {
                     mbar_wait(bar_acc_full + 8 * nas, ((acc_cnt + 1) >> 1) & 1, 8);
                     tc_fence_after();
                     tmem_ld_32x32(ntaddr, va);
                 }
-                epi_block<G, EXACT, 1>(ctx, vb);
+                if (biased) epi_block<G, EXACT, 1, true>(ctx, vb); else epi_block<G, EXACT, 1>(ctx, vb);
                 if (trc) p.trace[trb + 3] = clock64();               // arithmetic issued
                 FSTAMP(7);
                 if (kEpiPingPong) {

@@ -82,6 +82,18 @@ template <> struct Acc<false> {
         if (SLOT == 0) asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a0) : "f"(f0), "f"(f1));
         else           asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a1) : "f"(f0), "f"(f1));
     }
+    // Biased columns (kBiasCols): a fifth MMA (all-255 u8 x all-255 u8, K = 32) has added kBiasValue = 2 080 800 >=
+    // max |V'| to these accumulators, so the int32 is a positive number < 2^23 whose bit pattern, read as a float, is the
+    // denormal acc * 2^-149.  One FMA turns it into the voltage: fma(bits, 2^127, -kBiasValue * 2^-22) = V' * 2^-22,
+    // exactly -- on the FMA pipe, which has room, instead of the half-rate ALU pipe (I2FP) that bounds the epilogue.
+    // The squares then carry an exact factor 2^-44, folded into the output scale: results stay bit-identical.
+    template <int SLOT> __device__ __forceinline__ void add2b(int v0, int v1)
+    {
+        const unsigned long long k2 = 0x7F0000007F000000ull;      // {2^127, 2^127}
+        const unsigned long long c2 = 0xBEFE0100BEFE0100ull;      // {-2080800 * 2^-22, same}
+        if (SLOT == 0) asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 t, t, %3, %4; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a0) : "r"(v0), "r"(v1), "l"(k2), "l"(c2));
+        else           asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 t, t, %3, %4; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a1) : "r"(v0), "r"(v1), "l"(k2), "l"(c2));
+    }
     template <int NSLOT, bool HYB = false> __device__ __forceinline__ float sum() const
     {
         float a, b, c, d;
@@ -106,6 +118,14 @@ constexpr int kIntPeriodNZ = kIntPeriod > 0 ? kIntPeriod : 1;
 #define DSABF_EPI_XU 0
 #endif
 constexpr int kXuPeriod = DSABF_EPI_XU;
+// Columns [0, kBiasCols) of every 256-column accumulator tile of the resident-weights kernel get the bias MMA and the
+// FMA-pipe conversion (Acc<false>::add2b); a multiple of 64 = whole epilogue-warp slices.  0 = off.
+#ifndef DSABF_EPI_BIAS_COLS
+#define DSABF_EPI_BIAS_COLS 0
+#endif
+constexpr int kBiasCols = DSABF_EPI_BIAS_COLS;
+static_assert(kBiasCols % 64 == 0 && kBiasCols >= 0 && kBiasCols <= 256, "bias columns: whole 64-column slices");
+constexpr float kBiasUnscale = 17592186044416.0f;          // 2^44: the biased slices accumulate (V' * 2^-22)^2
 
 // Work-item geometry shared by all roles.
 struct Geom {
@@ -150,7 +170,7 @@ __device__ __forceinline__ void epi_store(EpiCtx<EXACT> &c, typename EpiCtx<EXAC
 // holding the other component (re rows = even lanes, im rows = odd lanes): even
 // lanes finish the even group of the pair, odd lanes the odd group, so one
 // shuffle yields two outputs and a warp stores 2 x 64 contiguous bytes.
-template <int G, bool EXACT, int BLK>
+template <int G, bool EXACT, int BLK, bool BIASED = false>
 __device__ __forceinline__ void epi_block(EpiCtx<EXACT> &c, const uint32_t (&v)[32])
 {
     constexpr int kGroups = kEpiCols / G;                 // groups per warp: 32,16,8,4,2,1
@@ -169,7 +189,10 @@ __device__ __forceinline__ void epi_block(EpiCtx<EXACT> &c, const uint32_t (&v)[
             const bool x0 = kXu && (jj % (kXu ? kXuPeriod : 1)) == (kXu ? kXuPeriod : 1) - 1;
             const bool x1 = kXu && ((jj + 1) % (kXu ? kXuPeriod : 1)) == (kXu ? kXuPeriod : 1) - 1;
             const int slot = (kSlots == 1 || (fpr & 1) == 0) ? 0 : 1;
-            if constexpr (!EXACT) {
+            if constexpr (!EXACT && BIASED) {
+                if (slot == 0) c.acc.template add2b<0>((int)v[jj], (int)v[jj + 1]);
+                else           c.acc.template add2b<1>((int)v[jj], (int)v[jj + 1]);
+            } else if constexpr (!EXACT) {
                 if (slot == 0) { if (x0) c.acc.template add2<0, true, false>((int)v[jj], (int)v[jj + 1]); else if (x1) c.acc.template add2<0, false, true>((int)v[jj], (int)v[jj + 1]); else c.acc.template add2<0>((int)v[jj], (int)v[jj + 1]); }
                 else           { if (x0) c.acc.template add2<1, true, false>((int)v[jj], (int)v[jj + 1]); else if (x1) c.acc.template add2<1, false, true>((int)v[jj], (int)v[jj + 1]); else c.acc.template add2<1>((int)v[jj], (int)v[jj + 1]); }
             } else {

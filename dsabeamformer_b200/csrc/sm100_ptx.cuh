@@ -160,6 +160,12 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(uint32_t M, uint32_t N)
     return (2u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// same with unsigned 8-bit A and B (format fields 0)
+__host__ __device__ constexpr uint32_t make_idesc_u8(uint32_t M, uint32_t N)
+{
+    return (2u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, issued by ONE thread.
 __device__ __forceinline__ void mma_i8_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
 {
@@ -256,6 +262,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         "}\n"
         : "=r"(ok)
         : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+    return ok != 0;
+}
+// One probe without a suspend-time hint (a single SYNCS.PHASECHK...TRYWAIT, no NANOSLEEP.SYNCS pair behind it).
+__device__ __forceinline__ bool mbar_try_wait_nohint(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
 }

@@ -460,12 +460,14 @@ def test_two_handles_two_threads_one_process(bf, oracle):
     assert not errors, errors
 
 
-@pytest.mark.parametrize("n_dm", [2, 3, 4, 5, 6, 7, 8])
-def test_dedisperse_few_trials_streaming(bf, oracle, n_dm):
+@pytest.mark.parametrize("n_dm,n_beams,n_t_out", [(2, 64, 2048), (3, 64, 2048), (4, 64, 2048), (5, 64, 2048), (6, 64, 2048), (7, 64, 2048), (8, 64, 2048),
+                                                   (2, 40, 3300), (8, 40, 3300), (4, 32, 4100)])
+def test_dedisperse_few_trials_streaming(bf, oracle, n_dm, n_beams, n_t_out, monkeypatch):
     """2..8 trials on a problem large enough for the one-pass streaming kernel (dedisperse_few_kernel: one thread per
     (time, 4 beams), n_dm accumulators): ragged channel count (tail loop), rows past the end of the power dropped."""
+    monkeypatch.setenv("DSABF_DEDISP_FORCE_FEW", "1")     # the dispatcher would take the staged kernel for the small cases
     rng = np.random.default_rng(40 + n_dm)
-    n_chan, n_beams, n_t_out = 67, 64, 2048
+    n_chan = 67
     dms = bf.dm_trials(2000.0, 2048)[[0, 3, 200, 600, 900, 1200, 1500, 1626][:n_dm]]
     freq = 1.53 - np.arange(n_chan) * (0.25 / n_chan)
     delay = bf.dm_delays(dms, freq)

@@ -21,4 +21,4 @@ def test_two_ranks_subbands_and_full_band_dedispersion():
                        capture_output=True, text=True, timeout=900)
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("vs oracle") == 3 * world          # sub-band, full-band dedispersion, scaled-array shard per rank
+    assert r.stdout.count("vs oracle") == 4 * world          # sub-band, full-band dedispersion, scaled-array shard, full trial list per rank

@@ -86,6 +86,32 @@ ok &= bool(worst <= 1e-6)
 print("rank %d scaled-array shard (256 ant x 2048 beams) vs oracle: max rel %.2e" % (rank, worst), flush=True)
 Bs.close()
 
+# BASELINE.json configs[4] as specified: the WHOLE trial list of sandbox/Dispersion Theory.ipynb (1627 trials, DM 0..2000,
+# unclamped delays: several hundred samples across the band) on the exchanged full band, every 50th trial and the
+# last one against the oracle
+dms_all = bf.dm_trials(2000.0, 2048)
+delay_all = bf.dm_delays(dms_all, freqs)
+T2 = int(delay_all.max()) + 96
+gen = torch.Generator(device="cuda"); gen.manual_seed(4242 + rank)
+try:
+    p2, h2 = D.alloc_symmetric_power(T2, 256, 256)
+    p2.copy_(torch.rand((T2, 256, 256), dtype=torch.float32, device="cuda", generator=gen) * 10)
+except Exception:
+    p2, h2 = torch.rand((T2, 256, 256), dtype=torch.float32, device="cuda", generator=gen) * 10, None
+torch.cuda.synchronize(); dist.barrier()
+ded_all = D.dedisperse_full_band(B, p2, delay_all, 96, symm_handle=h2).cpu().numpy()          # [1627][96][256/world]
+g2 = [torch.empty_like(p2) for _ in range(world)]
+dist.all_gather(g2, p2)
+full2 = torch.cat(g2, dim=1)[:, :, b0:b1].contiguous().cpu().numpy()
+del g2
+pick = np.unique(np.concatenate([np.arange(0, len(dms_all), 50), [len(dms_all) - 1]]))
+truth2 = O.dedisperse(full2, np.ascontiguousarray(delay_all[pick]), 96)
+rel2 = np.abs(ded_all[pick] - truth2) / np.maximum(np.abs(truth2), 1e-30)
+ok &= bool(rel2.max() <= max(5e-6, 1e-8 * full2.shape[1]))
+print("rank %d full trial list (%d trials, max delay %d samples, %s exchange) vs oracle on %d sampled trials: max rel %.2e"
+      % (rank, len(dms_all), int(delay_all.max()), "NVLink pull" if h2 is not None else "NCCL", len(pick), rel2.max()), flush=True)
+del full2, ded_all, p2
+
 # timing of the one exchange the path has, at the shard shape of configs[4]: [1024 times][256 ch][256 beams] per rank
 # -> all-to-all -> [1024][256*world][256/world], then 256 DM trials on the local beams (CUDA events, max over ranks)
 if world > 1:
