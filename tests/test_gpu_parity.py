@@ -478,3 +478,38 @@ def test_dedisperse_few_trials_streaming(bf, oracle, n_dm, n_beams, n_t_out, mon
     ref = oracle.dedisperse(power, delay, n_t_out)
     assert np.allclose(got, ref, rtol=2e-6, atol=1e-4)
     B.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_exchange_kernels_with_local_peers(bf, oracle, world):
+    """csrc/exchange.cu and the peer-segment dedispersion on ONE GPU: the `peers` are `world` separate buffers of this
+    device (the kernels only see pointers), every rank's view is computed in turn and compared with the definition
+        full_r[t][g*C + c][b] = power_g[t][c][r*Bs + b]
+    and with the oracle's DM-0 / single-trial dedispersion of that transpose.  Multi-GPU hardware runs of the same entry
+    points: tools/mgpu_check.py (smoke() on > 1 GPU, tests/test_multi_gpu.py)."""
+    import torch
+    rng = np.random.default_rng(60 + world)
+    T, C, NB = 40, 16, 64
+    Bs = NB // world
+    host = [rng.random((T, C, NB), dtype=np.float32) * 10 for _ in range(world)]
+    dev = [torch.from_numpy(h).cuda() for h in host]
+    ptrs = [d.data_ptr() for d in dev]
+    B = bf.Beamformer(debug=True, n_channels=1)
+    delay = (np.arange(world * C) % 7).astype(np.int32)             # one trial, delays 0..6
+    n_t_out = T - 6
+    st = torch.cuda.Stream()
+    for r in range(world):
+        full = torch.empty((T, C * world, Bs), dtype=torch.float32, device="cuda")
+        ded = torch.empty((n_t_out, Bs), dtype=torch.float32, device="cuda")
+        ded0 = torch.empty((T, Bs), dtype=torch.float32, device="cuda")
+        with torch.cuda.stream(st):
+            B.transpose_pull(ptrs, r, T, C, NB, full.data_ptr(), st.cuda_stream)
+            B.dedisperse_single_peers(ptrs, r, T, C, NB, delay, n_t_out, ded.data_ptr(), st.cuda_stream)
+            B.dedisperse_single_peers(ptrs, r, T, C, NB, np.zeros(world * C, dtype=np.int32), T, ded0.data_ptr(), st.cuda_stream)
+        torch.cuda.synchronize()
+        want = np.concatenate([h[:, :, r * Bs:(r + 1) * Bs] for h in host], axis=1)
+        assert np.array_equal(full.cpu().numpy(), want), (world, r)
+        ref = oracle.dedisperse(np.ascontiguousarray(want), delay[None, :], n_t_out)[0]
+        assert np.allclose(ded.cpu().numpy(), ref, rtol=2e-6), (world, r)
+        assert np.allclose(ded0.cpu().numpy(), want.sum(axis=1), rtol=2e-6), (world, r)
+    B.close()
