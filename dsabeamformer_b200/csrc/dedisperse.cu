@@ -307,27 +307,19 @@ cudaError_t launch_single(const Segments &seg, int n_t, int n_chan, int n_beams,
 // neighbouring times read the same rows for neighbouring trials) and otherwise come from L2, so HBM still sees every
 // row about once.  The staged kernel below needs ~8 trials per CTA to pay for its shared-memory staging and
 // barriers; under that it was latency-bound (1.3-1.6 TB/s of algorithmic bytes at 2-8 trials, r01).
-template <int ND, int UNROLL, bool WIDE_T>
-__global__ void __launch_bounds__(256)
+template <int ND, int UNROLL, int BLK>
+__global__ void __launch_bounds__(BLK)
 dedisperse_few_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_beams, const int32_t *__restrict__ delay, int n_t_out,
                       float *__restrict__ out)
 {
+    // Row-major items: a block of BLK threads covers BLK / (n_beams/4) consecutive output times of every beam quad, i.e. whole
+    // 1 KB rows at 256 beams.  BLK = 1024 (16 times x 256 beams): the ND trials of a channel read rows a few samples apart,
+    // which the other threads of the block have just pulled into L1, so L2 sees each row ~1.3 times instead of ND times.
+    // (A block shape of 32 times x 8 quads -- 128-byte row pieces -- was measured slower than this one: 3.2 vs 5.4 TB/s at 2 trials.)
     const int b4 = n_beams >> 2;
-    int t, q;
-    if (WIDE_T) {
-        // block = 32 output times x 8 beam quads (128 bytes of every row): the ND trials of a channel read rows only a
-        // few samples apart, so all but the first read of a row hit L1; a warp load covers 4 full 128-byte lines
-        const int qb = b4 >> 3;
-        const int tq = blockIdx.x % qb, tt = blockIdx.x / qb;
-        t = tt * 32 + (threadIdx.x >> 3);
-        q = tq * 8 + (threadIdx.x & 7);
-        if (t >= n_t_out) return;
-    } else {
-        const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-        if (idx >= (long long)n_t_out * b4) return;
-        t = (int)(idx / b4);
-        q = (int)(idx - (long long)t * b4);
-    }
+    const long long idx = (long long)blockIdx.x * BLK + threadIdx.x;
+    if (idx >= (long long)n_t_out * b4) return;
+    const int t = (int)(idx / b4), q = (int)(idx - (long long)t * b4);
     const float4 *p4 = reinterpret_cast<const float4 *>(power) + q;
     const size_t row4 = (size_t)b4;                                  // float4 per (time, channel) row
     float4 acc[ND];
@@ -366,20 +358,10 @@ cudaError_t launch_few(const float *d_power, int n_t, int n_chan, int n_beams, c
 {
     const long long n = (long long)n_t_out * (n_beams >> 2);
     constexpr int UNROLL = ND <= 2 ? 4 : (ND <= 4 ? 2 : 1);          // 8 float4 loads in flight per thread
-    // The 32-time x 8-quad block shape (rows shared through L1) measured slower than the plain row-major mapping on B200
-    // (2 trials, 2048 x 2048 x 256: 3.2 vs 5.4 TB/s of algorithmic bytes): L2 serves the re-reads well enough and the
-    // plain mapping streams 1 KB rows.  Kept behind DSABF_DEDISP_WIDE_T for the record.
-#ifdef DSABF_DEDISP_WIDE_T
-    constexpr bool kWide = true;
-#else
-    constexpr bool kWide = false;
-#endif
-    if (kWide && ((n_beams >> 2) & 7) == 0) {
-        const unsigned blocks = (unsigned)(((n_t_out + 31) / 32) * ((n_beams >> 2) >> 3));
-        dedisperse_few_kernel<ND, UNROLL, true><<<blocks, 256, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
-    } else {
-        dedisperse_few_kernel<ND, UNROLL, false><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
-    }
+    const char *e = getenv("DSABF_DEDISP_BLOCK");                      // experiment hook: 256 or 1024
+    const int blk = e ? atoi(e) : (ND <= 3 ? 1024 : 256);      // measured (2048 x 2048 x 256): 1024 is +4 % / +13 % at 2 / 3 trials, equal at 4, worse from 5 (registers)
+    if (blk == 1024) dedisperse_few_kernel<ND, UNROLL, 1024><<<(unsigned)((n + 1023) / 1024), 1024, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
+    else             dedisperse_few_kernel<ND, UNROLL, 256><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
     return cudaGetLastError();
 }
 
@@ -408,12 +390,12 @@ cudaError_t launch_dedisperse(const float *d_power, int n_t, int n_chan, int n_b
         return launch_single(seg, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
     }
     // 2..8 trials on a problem large enough to fill the machine with one thread per (time, 4 beams): one streaming pass
-    // (measured, 2048 channels x 256 beams: 2 trials 5.4 TB/s against 1.6 with the staged kernel at 2048 times; at 512 times
-    // or with 8 trials the staged kernel is as fast or faster -- too few threads / too many L2 reads per thread)
+    // (measured, 2048 times x 2048 channels x 256 beams, TB/s of algorithmic bytes: 2 trials 5.7, 3: 4.0, 4: 3.2, 6: 2.1, 8: 1.5 -- the
+    // staged kernel: 1.3-1.6 throughout; at 512 times, too few threads, the staged kernel is as fast or faster)
     const bool force_few = getenv("DSABF_DEDISP_FORCE_FEW") != nullptr;              // testing hook (read per call)
     const long long few_items = (long long)n_t_out * (n_beams >> 2);
     if (n_dm >= 2 && n_dm <= 8 && (n_beams & 3) == 0 && ((uintptr_t)d_power & 15) == 0 && ((uintptr_t)d_out & 15) == 0 &&
-        (force_few ? few_items >= 32768 : (n_dm <= 4 && few_items >= 98304))) {
+        (force_few ? few_items >= 32768 : few_items >= 98304)) {
         switch (n_dm) {
         case 2: return launch_few<2>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
         case 3: return launch_few<3>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);

@@ -77,6 +77,12 @@ constexpr bool kProducersOnTop = DSABF_ROLE_ORDER != 0;
 #define DSABF_EPI_PROBE 0
 #endif
 constexpr int kEpiProbe = DSABF_EPI_PROBE;
+// kEpiTrim (-DDSABF_EPI_TRIM): fewer non-arithmetic instructions per accumulator stage: the first probe of the full barrier
+// without a suspend hint (1 instruction instead of 3), the releasing lane picked with elect.sync instead of %laneid
+#ifndef DSABF_EPI_TRIM
+#define DSABF_EPI_TRIM 1
+#endif
+constexpr bool kEpiTrim = DSABF_EPI_TRIM != 0;
 #ifdef DSABF_BIAS_SKIP_MMA      // timing experiment only (wrong results): the FMA-pipe epilogue without the bias MMA
 constexpr bool kBiasSkipMma = true;
 #else
@@ -317,18 +323,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
         const uint32_t n_acc_total = (uint32_t)(item_end - item_begin) * (uint32_t)mt;
         const bool pp_second = (wc & 2) != 0;
         const uint32_t bar_go_mine = bar_epi_go + 8 * ew, bar_go_partner = bar_epi_go + 8 * (ew ^ 8);
+#if DSABF_EPI_PIPE != 0
         uint32_t va[32], vb[32];
+#endif
         bool probed = false;        // kEpiProbe: the barrier of the tile about to be loaded was already seen complete
         // kEpiPipe (-DDSABF_EPI_PIPE): how far the TMEM loads of the next M-tile run ahead of this tile's arithmetic
         //   0  load, wait, square, store -- strictly in sequence
         //   1  the next tile's loads are put in flight before this tile's last shuffle + store
         //   2  as 1, and its first 32 columns are loaded while this tile's second 32 columns are squared
+#if DSABF_EPI_PIPE != 0
         if (kEpiPipe > 0 && item_begin < item_end) {
             mbar_wait(bar_acc_full, 0, 8);
             tc_fence_after();
             tmem_ld_32x32(tbase_w, va);
             tmem_ld_32x32(tbase_w + 32, vb);
         }
+#endif
 #pragma unroll 1
         for (int item = item_begin; item < item_end; item++) {
             if (++t == g.n_tiles) { t = 0; f++; }
@@ -343,6 +353,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
 #pragma unroll 1
             for (int m = 0; m < mt; m++, acc_cnt++) {
                 const uint32_t as = acc_cnt & 1;
+#if DSABF_EPI_PIPE == 0
+                uint32_t va[32], vb[32];
+#endif
                 const bool trc = kTraceMode == 1 && p.trace && blockIdx.x == 0 && (ew == 0 || ew == 15) && lane == 0 && acc_cnt < 128;
                 const bool ftr = kTraceMode == 2 && p.trace && blockIdx.x == 0 && ew == DSABF_TRACE_EW && lane == 0 && acc_cnt < 128;
 #define FSTAMP(k) do { if (ftr) p.trace[acc_cnt * 16 + 4 + (k)] = clock64(); } while (0)
@@ -350,7 +363,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 if (trc) p.trace[trb + 0] = clock64();
                 FSTAMP(0);
                 if (kEpiPipe == 0) {
-                    if (!(kEpiProbe > 0 && probed)) mbar_wait(bar_acc_full + 8 * as, (acc_cnt >> 1) & 1, 8);
+                    if (kEpiTrim) { if (!mbar_try_wait_nohint(bar_acc_full + 8 * as, (acc_cnt >> 1) & 1)) mbar_wait(bar_acc_full + 8 * as, (acc_cnt >> 1) & 1, 8); }
+                    else if (!(kEpiProbe > 0 && probed)) mbar_wait(bar_acc_full + 8 * as, (acc_cnt >> 1) & 1, 8);
                     tc_fence_after();
                     FSTAMP(1);
                     tmem_ld_2x32_wait(tbase_w + as * kAccCols, va, vb);
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 tc_fence_before();
                 __syncwarp();
                 FSTAMP(3);
-                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+                if (kEpiTrim ? elect_one() : (lane == 0)) mbar_arrive(bar_acc_empty + 8 * as);
                 FSTAMP(4);
                 // ptxas sinks the arrive below all of the math that follows (it has no consumers), which
                 // keeps the TMEM stage -- and so the tensor pipe -- waiting.  A never-taken, runtime-opaque
@@ -406,7 +420,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                     tc_fence_after();
                     tmem_ld_32x32(ntaddr, va);
                 }
-                if (biased) epi_block<G, EXACT, 1, true>(ctx, vb); else epi_block<G, EXACT, 1>(ctx, vb);
+                constexpr bool kDefer = kEpiPipe != 0;          // only the prefetching variants split off the last shuffle + store
+                if (biased) epi_block<G, EXACT, 1, true, kDefer>(ctx, vb); else epi_block<G, EXACT, 1, false, kDefer>(ctx, vb);
                 if (trc) p.trace[trb + 3] = clock64();               // arithmetic issued
                 FSTAMP(7);
                 if (kEpiPingPong) {
@@ -421,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                     tmem_ld_32x32(ntaddr, va);
                     tmem_ld_32x32(ntaddr + 32, vb);
                 }
-                epi_finish<G, EXACT>(ctx);
+                if (kDefer) epi_finish<G, EXACT>(ctx);
                 FSTAMP(9);
                 out_item += 64;                                      // next M-tile = next 64 beams
                 if (EXACT) { if (pp_item) pp_item += 64; }

@@ -274,7 +274,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_big_kernel(const F
                 ctx.pp = pp_item;
                 epi_block<G, EXACT, 0>(ctx, va);
                 epi_block<G, EXACT, 1>(ctx, vb);
-                epi_finish<G, EXACT>(ctx);
                 out_item += 64;
                 if (EXACT) { if (pp_item) pp_item += 64; }
             }

@@ -121,7 +121,10 @@ constexpr int kXuPeriod = DSABF_EPI_XU;
 // Columns [0, kBiasCols) of every 256-column accumulator tile of the resident-weights kernel get the bias MMA and the
 // FMA-pipe conversion (Acc<false>::add2b); a multiple of 64 = whole epilogue-warp slices.  0 = off.
 #ifndef DSABF_EPI_BIAS_COLS
-#define DSABF_EPI_BIAS_COLS 0
+#define DSABF_EPI_BIAS_COLS 256      // all four slices: measured 1-2 % (observation shape) to 5 % (DEBUG shape) faster than I2FP, bit-identical
+#endif
+#if DSABF_EPI_BIAS_COLS > 0 && defined(__CUDA_FTZ)
+#error "the bias-MMA epilogue reads int32 accumulators as denormal floats: do not compile with -ftz=true / -use_fast_math"
 #endif
 constexpr int kBiasCols = DSABF_EPI_BIAS_COLS;
 static_assert(kBiasCols % 64 == 0 && kBiasCols >= 0 && kBiasCols <= 256, "bias columns: whole 64-column slices");
@@ -170,7 +173,7 @@ __device__ __forceinline__ void epi_store(EpiCtx<EXACT> &c, typename EpiCtx<EXAC
 // holding the other component (re rows = even lanes, im rows = odd lanes): even
 // lanes finish the even group of the pair, odd lanes the odd group, so one
 // shuffle yields two outputs and a warp stores 2 x 64 contiguous bytes.
-template <int G, bool EXACT, int BLK, bool BIASED = false>
+template <int G, bool EXACT, int BLK, bool BIASED = false, bool DEFER = false>
 __device__ __forceinline__ void epi_block(EpiCtx<EXACT> &c, const uint32_t (&v)[32])
 {
     constexpr int kGroups = kEpiCols / G;                 // groups per warp: 32,16,8,4,2,1
@@ -208,13 +211,19 @@ __device__ __forceinline__ void epi_block(EpiCtx<EXACT> &c, const uint32_t (&v)[
             else                sgrp = c.acc.template sum<kSlots>();
             c.acc.zero();
             if (kGroups == 1) {
-                c.def_mine = sgrp;                 // finished in epi_finish()
+                if (DEFER) {
+                    c.def_mine = sgrp;             // finished in epi_finish()
+                } else {
+                    const auto tot = sgrp + __shfl_xor_sync(0xffffffffu, sgrp, 1);
+                    // single group: only the even lanes (vg_lane = valid - 0) store
+                    if (!c.lane_odd) epi_store<EXACT>(c, tot, 0);
+                }
             } else if ((grp & 1) == 0) {
                 c.pend = sgrp;
             } else {
                 const auto send = c.lane_odd ? c.pend : sgrp;
                 const auto mine = c.lane_odd ? sgrp : c.pend;
-                if (grp == kGroups - 1) {          // last pair of the tile: deferred, so that the caller can put the
+                if (DEFER && grp == kGroups - 1) { // last pair of the tile: deferred, so that the caller can put the
                     c.def_mine = mine;             // next tile's TMEM loads in flight before the shuffle and the store
                     c.def_send = send;
                 } else {

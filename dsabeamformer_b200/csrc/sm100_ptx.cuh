@@ -280,6 +280,19 @@ __device__ __forceinline__ bool mbar_try_wait_nohint(uint32_t bar, uint32_t pari
         : "memory");
     return ok != 0;
 }
+// true in exactly one lane of a converged warp, without reading %laneid (SASS: ELECT)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok));
+    return ok != 0;
+}
 // BACKOFF_NS > 0: sleep that long between probes.  For waits that are expected to be long (a slot
 // freed once per work item) -- a hinted try_wait alone wakes up at every arrival on the barrier and
 // the probing warp then competes for issue slots with the epilogue warps of its sub-partition.
