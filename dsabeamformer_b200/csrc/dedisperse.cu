@@ -28,8 +28,14 @@ namespace {
 constexpr int DD_TT = 32;        // output times per CTA
 constexpr int DD_BB = 32;        // beams per CTA (one per lane)
 constexpr int DD_DMS = 8;        // DM trials per CTA (one per warp)
-constexpr int DD_FC = 4;         // channels per staged chunk
-constexpr int DD_WIN = 64;       // staged rows per channel: (dmax - dmin) + 32 <= 64, else direct global reads
+#ifndef DSABF_DD_FC
+#define DSABF_DD_FC 4
+#endif
+#ifndef DSABF_DD_WIN
+#define DSABF_DD_WIN 64
+#endif
+constexpr int DD_FC = DSABF_DD_FC;   // channels per staged chunk
+constexpr int DD_WIN = DSABF_DD_WIN; // staged rows per channel: (dmax - dmin) + 32 <= DD_WIN, else direct global reads
 constexpr int DD_THREADS = DD_DMS * 32;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
