@@ -332,19 +332,36 @@ dedisperse_few_kernel(const float *__restrict__ power, int n_t, int n_chan, int 
 #pragma unroll
     for (int d = 0; d < ND; d++) acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
     int f = 0;
+    // UNROLL channels per step.  Trial 0's rows are loaded for all of them at once (UNROLL independent 16-byte loads in
+    // flight); every further trial reuses the row held for the previous trial whenever its delay at that channel is the same
+    // -- neighbouring trials of a fine DM grid differ at few channels, at none at the top of the band -- and reloads it
+    // otherwise (from L1 / L2: a neighbouring thread has just read that row).  The delays are the same for every thread, so
+    // the branches are uniform; each trial still adds its channels in ascending order (results unchanged bit for bit).
+    const bool vec_delay = UNROLL == 4 && (n_chan & 3) == 0 && ((uintptr_t)delay & 15) == 0;
     for (; f + UNROLL <= n_chan; f += UNROLL) {
-        float4 v[UNROLL][ND];
+        float4 cur[UNROLL];
+        int dlp[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++)
+        for (int d = 0; d < ND; d++) {
+            int dl[UNROLL];
+            if (vec_delay) {
+                const int4 q4 = __ldg(reinterpret_cast<const int4 *>(delay + (size_t)d * n_chan + f));
+                dl[0] = q4.x; dl[1 % UNROLL] = q4.y; dl[2 % UNROLL] = q4.z; dl[3 % UNROLL] = q4.w;
+            } else {
 #pragma unroll
-            for (int d = 0; d < ND; d++) {
-                const int tt = t + __ldg(delay + (size_t)d * n_chan + f + u);
-                v[u][d] = (tt < n_t) ? __ldg(p4 + ((size_t)tt * n_chan + f + u) * row4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < UNROLL; u++) dl[u] = __ldg(delay + (size_t)d * n_chan + f + u);
             }
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++)
+            for (int u = 0; u < UNROLL; u++) {
+                if (d == 0 || dl[u] != dlp[u]) {
+                    const int tt = t + dl[u];
+                    cur[u] = (tt < n_t) ? __ldg(p4 + ((size_t)tt * n_chan + f + u) * row4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dlp[u] = dl[u];
+                }
+            }
 #pragma unroll
-            for (int d = 0; d < ND; d++) { acc[d].x += v[u][d].x; acc[d].y += v[u][d].y; acc[d].z += v[u][d].z; acc[d].w += v[u][d].w; }
+            for (int u = 0; u < UNROLL; u++) { acc[d].x += cur[u].x; acc[d].y += cur[u].y; acc[d].z += cur[u].z; acc[d].w += cur[u].w; }
+        }
     }
     for (; f < n_chan; f++)
 #pragma unroll
@@ -359,16 +376,27 @@ dedisperse_few_kernel(const float *__restrict__ power, int n_t, int n_chan, int 
     for (int d = 0; d < ND; d++) reinterpret_cast<float4 *>(out)[((size_t)d * n_t_out + t) * b4 + q] = acc[d];
 }
 
+template <int ND, int UNROLL>
+cudaError_t launch_few_u(int blk, const float *d_power, int n_t, int n_chan, int n_beams, const int32_t *d_delay, int n_t_out, float *d_out, cudaStream_t stream)
+{
+    const long long n = (long long)n_t_out * (n_beams >> 2);
+    if (blk == 1024)     dedisperse_few_kernel<ND, UNROLL, 1024><<<(unsigned)((n + 1023) / 1024), 1024, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
+    else if (blk == 512) dedisperse_few_kernel<ND, UNROLL, 512><<<(unsigned)((n + 511) / 512), 512, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
+    else                 dedisperse_few_kernel<ND, UNROLL, 256><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
+    return cudaGetLastError();
+}
+
 template <int ND>
 cudaError_t launch_few(const float *d_power, int n_t, int n_chan, int n_beams, const int32_t *d_delay, int n_t_out, float *d_out, cudaStream_t stream)
 {
-    const long long n = (long long)n_t_out * (n_beams >> 2);
-    constexpr int UNROLL = ND <= 2 ? 4 : (ND <= 4 ? 2 : 1);          // 8 float4 loads in flight per thread
-    const char *e = getenv("DSABF_DEDISP_BLOCK");                      // experiment hook: 256 or 1024
-    const int blk = e ? atoi(e) : (ND <= 3 ? 1024 : 256);      // measured (2048 x 2048 x 256): 1024 is +4 % / +13 % at 2 / 3 trials, equal at 4, worse from 5 (registers)
-    if (blk == 1024) dedisperse_few_kernel<ND, UNROLL, 1024><<<(unsigned)((n + 1023) / 1024), 1024, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
-    else             dedisperse_few_kernel<ND, UNROLL, 256><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out);
-    return cudaGetLastError();
+    const char *e = getenv("DSABF_DEDISP_BLOCK");                      // experiment hooks: block size 256 / 512 / 1024, channels per step 2 / 4
+    const char *eu = getenv("DSABF_DEDISP_UNROLL");
+    // measured, 2048 times x 2048 channels x 256 beams, neighbouring trials (profiles/r02_dedisperse_timing.jsonl, group 4), TB/s of
+    // algorithmic bytes at the setting chosen here: 2: 7.0, 3: 6.5, 4: 6.2, 5: 5.3, 6: 4.0, 7: 3.6, 8: 3.3
+    const int blk = e ? atoi(e) : (ND <= 4 || ND == 8 ? 1024 : (ND == 7 ? 512 : 256));
+    const int unroll = eu ? atoi(eu) : (ND == 6 ? 2 : 4);
+    if (unroll == 2) return launch_few_u<ND, 2>(blk, d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
+    return launch_few_u<ND, 4>(blk, d_power, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
 }
 
 template <int STAGES, int TSPLIT>
@@ -396,7 +424,8 @@ cudaError_t launch_dedisperse(const float *d_power, int n_t, int n_chan, int n_b
         return launch_single(seg, n_t, n_chan, n_beams, d_delay, n_t_out, d_out, stream);
     }
     // 2..8 trials on a problem large enough to fill the machine with one thread per (time, 4 beams): one streaming pass
-    // (measured, 2048 times x 2048 channels x 256 beams, TB/s of algorithmic bytes: 2 trials 5.7, 3: 4.0, 4: 3.2, 6: 2.1, 8: 1.5 -- the
+    // (measured, 2048 times x 2048 channels x 256 beams, TB/s of algorithmic bytes, neighbouring trials: 2 trials 7.0, 3: 6.5, 4: 6.2,
+    // 5: 5.3, 6: 4.0, 7: 3.6, 8: 3.3; every 100th trial of the list, i.e. no shared rows: 5.2, 3.5, 3.3, 1.3 (6), 1.7 (8) -- the
     // staged kernel: 1.3-1.6 throughout; at 512 times, too few threads, the staged kernel is as fast or faster)
     const bool force_few = getenv("DSABF_DEDISP_FORCE_FEW") != nullptr;              // testing hook (read per call)
     const long long few_items = (long long)n_t_out * (n_beams >> 2);

@@ -13,7 +13,8 @@ B = bf.Beamformer(debug=True, n_channels=1)
 n_t, n_chan, n_beams = int(os.environ.get("DD_T", 1024)), 2048, int(os.environ.get("DD_B", 32))
 n_dm = int(os.environ.get("DD_NDM", 256))
 freq = 1.53 - (np.arange(n_chan) + 0.0) * (0.25 / 2048)
-dms = O.dm_trials(2000.0, 2048)[:n_dm]
+stride = int(os.environ.get("DD_STRIDE", 1))        # 1: neighbouring trials of the list (equal delays at most channels); > 1: every stride-th
+dms = O.dm_trials(2000.0, 2048)[::stride][:n_dm]
 delay = O.dm_delays(dms, freq)
 n_t_out = n_t - int(delay.max())
 assert n_t_out > 0, (n_t, delay.max())
@@ -39,5 +40,5 @@ adds = float(n_dm) * n_chan * n_beams * n_t_out
 sub = O.dedisperse(power[:, :, :2].cpu().numpy(), delay[:3], n_t_out)
 got = out[:3, :, :2].cpu().numpy()
 print(json.dumps({"kernel": "dedisperse_kernel", "n_t": n_t, "n_chan": n_chan, "n_beams": n_beams, "n_dm": n_dm, "n_t_out": n_t_out,
-                  "max_delay": int(delay.max()), "ms": ms, "ms_batches": [round(b, 4) for b in batches], "algorithmic_GB_s": algo / ms * 1e-6, "Gadds_s": adds / ms * 1e-6,
+                  "max_delay": int(delay.max()), "dm_stride": stride, "ms": ms, "ms_batches": [round(b, 4) for b in batches], "algorithmic_GB_s": algo / ms * 1e-6, "Gadds_s": adds / ms * 1e-6,
                   "max_rel_vs_oracle": float((np.abs(got - sub) / np.maximum(np.abs(sub), 1e-30)).max())}))
