@@ -6,18 +6,18 @@
 //     out[d][t][b] = sum_f power[t + delay[d][f]][f][b]
 // power is the fused kernel's output layout [time][channel][beam] (beam fastest).
 //
-// Blocking.  One CTA = 8 warps owns (32 output times) x (32 beams) x (8 DM trials): warp w
-// accumulates trial d0+w, lane l beam b0+l, 32 time accumulators per thread in registers.
+// Blocking.  One CTA = 8 warps owns (DD_TT = 64 output times) x (32 beams) x (8 DM trials): a warp
+// accumulates a pair of adjacent trials over half of the times, lane l beam b0+l, 64 accumulators per thread.
 // Channels are processed in chunks of 4.  Neighbouring DM trials have nearly equal delays,
 // so for one channel the union of the rows the 8 trials need is a short window
-// [t0+dmin, t0+dmax+32) of 128-byte rows; the window of each channel of the chunk is staged in
+// [t0+dmin, t0+dmax+DD_TT) of 128-byte rows; the window of each channel of the chunk is staged in
 // shared memory with cp.async (double-buffered against the arithmetic on the previous chunk)
 // and every warp then reads its 32 rows from there (consecutive lanes = consecutive beams:
 // conflict-free).  Each staged value is used by up to 8 trials, so global traffic per add is
 // ~1/16 of a float; every add costs one 4-byte shared-memory read per lane, which is the
 // structural bound of brute-force dedispersion (32 adds/clk/SM).  With few trials the kernel is
 // HBM-bound (power read once), with many it is shared-memory-bound.  Fewer than 8 trials: the warps
-// split the 32 output times (TSPLIT); a grid under two waves runs a 4-deep cp.async pipeline (STAGES).
+// split the output times (TSPLIT); a grid under two waves runs a 4-deep cp.async pipeline (STAGES).
 #include <cstdint>
 #include <cstdlib>
 #include "fused_beamform.cuh"
@@ -25,17 +25,20 @@
 namespace dsabf {
 namespace {
 
-constexpr int DD_TT = 32;        // output times per CTA
+#ifndef DSABF_DD_TT
+#define DSABF_DD_TT 64           // 64 x 96 rows against 32 x 64: staging, metadata and barriers per add halve (+10..14 % at 64 / 256 / 1627 trials)
+#endif
+constexpr int DD_TT = DSABF_DD_TT;   // output times per CTA
 constexpr int DD_BB = 32;        // beams per CTA (one per lane)
 constexpr int DD_DMS = 8;        // DM trials per CTA (one per warp)
 #ifndef DSABF_DD_FC
 #define DSABF_DD_FC 4
 #endif
 #ifndef DSABF_DD_WIN
-#define DSABF_DD_WIN 64
+#define DSABF_DD_WIN 96
 #endif
 constexpr int DD_FC = DSABF_DD_FC;   // channels per staged chunk
-constexpr int DD_WIN = DSABF_DD_WIN; // staged rows per channel: (dmax - dmin) + 32 <= DD_WIN, else direct global reads
+constexpr int DD_WIN = DSABF_DD_WIN; // staged rows per channel: (dmax - dmin) + DD_TT <= DD_WIN, else direct global reads
 constexpr int DD_THREADS = DD_DMS * 32;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
@@ -64,7 +67,7 @@ dedisperse_kernel(const float *__restrict__ power, int n_t, int n_chan, int n_be
     // DM slab fastest: the CTAs that read the same (time, beam) window of the power run together and share it in L2
     const int d0 = blockIdx.x * (DD_DMS / TSPLIT), t0 = blockIdx.y * DD_TT, b0 = blockIdx.z * DD_BB;
     const int nd = min(DD_DMS / TSPLIT, n_dm - d0);
-    // With fewer than 8 trials per CTA the warps split the 32 output times instead (TSPLIT slices of TW times)
+    // With fewer than 8 trials per CTA the warps split the output times instead (TSPLIT slices of TW times)
     constexpr int TW = DD_TT / TSPLIT;
     const int dw = warp % (DD_DMS / TSPLIT), tofs = (warp / (DD_DMS / TSPLIT)) * TW;
     const bool my_dm = dw < nd;
