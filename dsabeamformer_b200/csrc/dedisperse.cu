@@ -40,6 +40,7 @@ constexpr int DD_DMS = 8;        // DM trials per CTA (one per warp)
 constexpr int DD_FC = DSABF_DD_FC;   // channels per staged chunk
 constexpr int DD_WIN = DSABF_DD_WIN; // staged rows per channel: (dmax - dmin) + DD_TT <= DD_WIN, else direct global reads
 constexpr int DD_THREADS = DD_DMS * 32;
+static_assert(DD_FC * DD_DMS == 32, "the chunk metadata is computed by exactly one full warp (full-mask shuffles): DD_FC * DD_DMS must be 32");
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
