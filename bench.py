@@ -294,6 +294,15 @@ class Ranks:
     def sum(self, x):
         return self._red(x, self.dist.ReduceOp.SUM) if self.dist else x
 
+    def gather(self, x, rank):
+        """x of every rank, in rank order (one all_reduce of a one-hot vector: the same primitive as max / sum)"""
+        if not self.dist:
+            return [float(x)]
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device="cuda")
+        t[rank] = float(x)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
 
 def copy_ceiling(torch, ranks, h_in, d_in, d_out, h_out, reps):
     """Bare pinned cudaMemcpyAsync of one step's bytes, H2D and D2H on two streams at once, on every rank at the same
@@ -530,6 +539,10 @@ def run_ours(args):
     launches_value = B.kernel_launches - launches0
     dev_ms_max = ranks.max(dev_ms)
     value = world * samples_per_step * args.steps / (dev_ms_max * 1e-3)
+    # per rank: the step time and the kernel's own average launch time -- tells a slow GPU (both up) from a host that
+    # fell behind with the launches (step up, kernel not); `value` uses the slowest rank
+    per_rank = {"ms_per_step": [round(v / args.steps, 4) for v in ranks.gather(dev_ms, rank)],
+                "fused_kernel_ms": [round(v, 5) for v in ranks.gather(kern_ms, rank)]}
 
     # --- e2e: host buffers through the streaming C ABI (H2D + kernel + D2H per block)
     h_in = torch.empty(step_in_bytes, dtype=torch.uint8).pin_memory()
@@ -634,6 +647,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
             "config": CONFIG,
+            "per_rank": per_rank,
             "value_sustained": sustained["value"] if sustained else None,
             "sustained": sustained,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": step_in_bytes, "d2h_bytes_per_step": step_out_bytes,
