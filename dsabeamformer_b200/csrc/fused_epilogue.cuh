@@ -61,32 +61,20 @@ template <> struct Acc<true> {
 template <> struct Acc<false> {
     using sum_t = float;
     unsigned long long a0, a1;     // two packed float2 accumulators
-    long long si;                  // integer side accumulator of the hybrid epilogue (kIntPeriod > 0)
-    __device__ __forceinline__ void zero() { a0 = 0ull; a1 = 0ull; si = 0; }
-    // Hybrid: every kIntPeriod-th pair of columns is squared on the FMA pipe as integers (IMAD.WIDE, no
-    // conversion) instead of I2FP (ALU pipe, half rate) + FFMA2, so that the two pipes share the work.
-    __device__ __forceinline__ void addi(int v0, int v1)
-    {
-        asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(si) : "r"(v0));
-        asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(si) : "r"(v1));
-    }
-    // XU0 / XU1: convert that element with cvt.rp (SASS I2F.RP, the XU pipe) instead of cvt.rn (I2FP, the
-    // half-rate ALU pipe that bounds this epilogue).  |v| < 2^24, so every rounding mode gives the same float.
-    template <int SLOT, bool XU0 = false, bool XU1 = false> __device__ __forceinline__ void add2(int v0, int v1)
+    __device__ __forceinline__ void zero() { a0 = 0ull; a1 = 0ull; }
+    template <int SLOT> __device__ __forceinline__ void add2(int v0, int v1)
     {
         float f0, f1;
-        if (XU0) asm("cvt.rp.f32.s32 %0, %1;" : "=f"(f0) : "r"(v0));
-        else     asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f0) : "r"(v0));
-        if (XU1) asm("cvt.rp.f32.s32 %0, %1;" : "=f"(f1) : "r"(v1));
-        else     asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f1) : "r"(v1));
+        asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f0) : "r"(v0));
+        asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f1) : "r"(v1));
         if (SLOT == 0) asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a0) : "f"(f0), "f"(f1));
         else           asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a1) : "f"(f0), "f"(f1));
     }
     // Biased columns (kBiasCols): a fifth MMA (all-255 u8 x all-255 u8, K = 32) has added kBiasValue = 2 080 800 >=
     // max |V'| to these accumulators, so the int32 is a positive number < 2^23 whose bit pattern, read as a float, is the
     // denormal acc * 2^-149.  One FMA turns it into the voltage: fma(bits, 2^127, -kBiasValue * 2^-22) = V' * 2^-22,
-    // exactly -- on the FMA pipe, which has room, instead of the half-rate ALU pipe (I2FP) that bounds the epilogue.
-    // The squares then carry an exact factor 2^-44, folded into the output scale: results stay bit-identical.
+    // exactly -- on the FMA pipe instead of the half-rate ALU pipe (I2FP).  The squares then carry an exact factor
+    // 2^-44, folded into the output scale: results stay bit-identical to the I2FP path.
     template <int SLOT> __device__ __forceinline__ void add2b(int v0, int v1)
     {
         const unsigned long long k2 = 0x7F0000007F000000ull;      // {2^127, 2^127}
@@ -94,30 +82,16 @@ template <> struct Acc<false> {
         if (SLOT == 0) asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 t, t, %3, %4; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a0) : "r"(v0), "r"(v1), "l"(k2), "l"(c2));
         else           asm("{.reg .b64 t; mov.b64 t, {%1, %2}; fma.rn.f32x2 t, t, %3, %4; fma.rn.f32x2 %0, t, t, %0;}" : "+l"(a1) : "r"(v0), "r"(v1), "l"(k2), "l"(c2));
     }
-    template <int NSLOT, bool HYB = false> __device__ __forceinline__ float sum() const
+    template <int NSLOT> __device__ __forceinline__ float sum() const
     {
         float a, b, c, d;
         asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(a0));
         if (NSLOT == 1) return a + b;
         asm("mov.b64 {%0, %1}, %2;" : "=f"(c), "=f"(d) : "l"(a1));
-        if (HYB) return ((a + b) + (c + d)) + (float)si;      // every term is an integer multiple of 256: exact below 2^24 * 256
         return (a + b) + (c + d);
     }
 };
 
-// Share of the square-accumulates done as integers: one pair of columns in every kIntPeriod (0 = none).
-// Only for groups of >= 16 columns (the int64 side sum costs one I2F.S64 + FADD per group).
-#ifndef DSABF_EPI_INT
-#define DSABF_EPI_INT 0
-#endif
-constexpr int kIntPeriod = DSABF_EPI_INT;
-constexpr int kIntPeriodNZ = kIntPeriod > 0 ? kIntPeriod : 1;
-// Share of the int32 -> float conversions moved from the ALU pipe (I2FP) to the XU pipe (I2F.RP): one column
-// in every kXuPeriod (0 = none).
-#ifndef DSABF_EPI_XU
-#define DSABF_EPI_XU 0
-#endif
-constexpr int kXuPeriod = DSABF_EPI_XU;
 // Columns [0, kBiasCols) of every 256-column accumulator tile of the resident-weights kernel get the bias MMA and the
 // FMA-pipe conversion (Acc<false>::add2b); a multiple of 64 = whole epilogue-warp slices.  0 = off.
 #ifndef DSABF_EPI_BIAS_COLS
@@ -149,7 +123,6 @@ template <bool EXACT> struct EpiCtx {
     long long *pp;        // same for the exact-power dump (nullptr = off)
     size_t pair_stride;   // elements between consecutive group pairs = 2 output times
     float scale;
-    sum_t def_mine, def_send;   // last group pair of the warp's 64 columns: finished by epi_finish()
 };
 
 // Store the finished output of group pair PAIR (compile-time) and advance the pointers.
@@ -173,83 +146,43 @@ __device__ __forceinline__ void epi_store(EpiCtx<EXACT> &c, typename EpiCtx<EXAC
 // holding the other component (re rows = even lanes, im rows = odd lanes): even
 // lanes finish the even group of the pair, odd lanes the odd group, so one
 // shuffle yields two outputs and a warp stores 2 x 64 contiguous bytes.
-template <int G, bool EXACT, int BLK, bool BIASED = false, bool DEFER = false>
+// BIASED: the accumulators carry the bias MMA's offset (Acc<false>::add2b).
+template <int G, bool EXACT, int BLK, bool BIASED = false>
 __device__ __forceinline__ void epi_block(EpiCtx<EXACT> &c, const uint32_t (&v)[32])
 {
     constexpr int kGroups = kEpiCols / G;                 // groups per warp: 32,16,8,4,2,1
     constexpr int kSlots = (G >= 4) ? 2 : 1;              // packed accumulator slots in use
-    constexpr bool kHyb = !EXACT && kIntPeriod > 0 && G >= 16;
 #pragma unroll
     for (int jj = 0; jj < 32; jj += 2) {
         const int pr = jj >> 1;                           // pair index inside this block of 32 columns
-        bool as_int = false;
-        if constexpr (kHyb) as_int = (pr % kIntPeriodNZ) == kIntPeriodNZ - 1;
-        if (as_int) {
-            if constexpr (kHyb) c.acc.addi((int)v[jj], (int)v[jj + 1]);
+        const int slot = (kSlots == 1 || (pr & 1) == 0) ? 0 : 1;
+        if constexpr (!EXACT && BIASED) {
+            if (slot == 0) c.acc.template add2b<0>((int)v[jj], (int)v[jj + 1]);
+            else           c.acc.template add2b<1>((int)v[jj], (int)v[jj + 1]);
         } else {
-            const int fpr = kHyb ? pr - pr / kIntPeriodNZ : pr;      // index among the float pairs
-            constexpr bool kXu = !EXACT && kXuPeriod > 0;
-            const bool x0 = kXu && (jj % (kXu ? kXuPeriod : 1)) == (kXu ? kXuPeriod : 1) - 1;
-            const bool x1 = kXu && ((jj + 1) % (kXu ? kXuPeriod : 1)) == (kXu ? kXuPeriod : 1) - 1;
-            const int slot = (kSlots == 1 || (fpr & 1) == 0) ? 0 : 1;
-            if constexpr (!EXACT && BIASED) {
-                if (slot == 0) c.acc.template add2b<0>((int)v[jj], (int)v[jj + 1]);
-                else           c.acc.template add2b<1>((int)v[jj], (int)v[jj + 1]);
-            } else if constexpr (!EXACT) {
-                if (slot == 0) { if (x0) c.acc.template add2<0, true, false>((int)v[jj], (int)v[jj + 1]); else if (x1) c.acc.template add2<0, false, true>((int)v[jj], (int)v[jj + 1]); else c.acc.template add2<0>((int)v[jj], (int)v[jj + 1]); }
-                else           { if (x0) c.acc.template add2<1, true, false>((int)v[jj], (int)v[jj + 1]); else if (x1) c.acc.template add2<1, false, true>((int)v[jj], (int)v[jj + 1]); else c.acc.template add2<1>((int)v[jj], (int)v[jj + 1]); }
-            } else {
-                if (slot == 0) c.acc.template add2<0>((int)v[jj], (int)v[jj + 1]);
-                else           c.acc.template add2<1>((int)v[jj], (int)v[jj + 1]);
-            }
+            if (slot == 0) c.acc.template add2<0>((int)v[jj], (int)v[jj + 1]);
+            else           c.acc.template add2<1>((int)v[jj], (int)v[jj + 1]);
         }
         const int cl = BLK * 32 + jj + 1;          // last column handled so far (compile-time after unrolling)
         if (((cl + 1) % G) == 0) {
             const int grp = cl / G;
-            typename EpiCtx<EXACT>::sum_t sgrp;
-            if constexpr (kHyb) sgrp = c.acc.template sum<kSlots, true>();
-            else                sgrp = c.acc.template sum<kSlots>();
+            const typename EpiCtx<EXACT>::sum_t sgrp = c.acc.template sum<kSlots>();
             c.acc.zero();
             if (kGroups == 1) {
-                if (DEFER) {
-                    c.def_mine = sgrp;             // finished in epi_finish()
-                } else {
-                    const auto tot = sgrp + __shfl_xor_sync(0xffffffffu, sgrp, 1);
-                    // single group: only the even lanes (vg_lane = valid - 0) store
-                    if (!c.lane_odd) epi_store<EXACT>(c, tot, 0);
-                }
+                const auto tot = sgrp + __shfl_xor_sync(0xffffffffu, sgrp, 1);
+                // single group: only the even lanes (vg_lane = valid - 0) store
+                if (!c.lane_odd) epi_store<EXACT>(c, tot, 0);
             } else if ((grp & 1) == 0) {
                 c.pend = sgrp;
             } else {
                 const auto send = c.lane_odd ? c.pend : sgrp;
                 const auto mine = c.lane_odd ? sgrp : c.pend;
-                if (DEFER && grp == kGroups - 1) { // last pair of the tile: deferred, so that the caller can put the
-                    c.def_mine = mine;             // next tile's TMEM loads in flight before the shuffle and the store
-                    c.def_send = send;
-                } else {
-                    const auto tot = mine + __shfl_xor_sync(0xffffffffu, send, 1);
-                    epi_store<EXACT>(c, tot, grp - 1);
-                }
+                const auto tot = mine + __shfl_xor_sync(0xffffffffu, send, 1);
+                epi_store<EXACT>(c, tot, grp - 1);
             }
         }
     }
 }
-
-// Exchange, scale and store of the last group pair of a tile (see epi_block).
-template <int G, bool EXACT>
-__device__ __forceinline__ void epi_finish(EpiCtx<EXACT> &c)
-{
-    constexpr int kGroups = kEpiCols / G;
-    if (kGroups == 1) {
-        const auto tot = c.def_mine + __shfl_xor_sync(0xffffffffu, c.def_mine, 1);
-        // single group: only the even lanes (vg_lane = valid - 0) store
-        if (!c.lane_odd) epi_store<EXACT>(c, tot, 0);
-    } else {
-        const auto tot = c.def_mine + __shfl_xor_sync(0xffffffffu, c.def_send, 1);
-        epi_store<EXACT>(c, tot, kGroups - 2);
-    }
-}
-
 
 }  // namespace fused
 }  // namespace dsabf

@@ -1,5 +1,5 @@
 """Fine clock64 trace of ONE epilogue warp (library built with -DDSABF_TRACE=2 [-DDSABF_TRACE_EW=n]; DSABF_LIB selects it):
-ten stamps per accumulator stage.  Prints the mean interval between consecutive stamps over stages 24..119."""
+eight stamps per accumulator stage.  Prints the mean interval between consecutive stamps over stages 24..119."""
 import sys, os, ctypes
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -13,17 +13,17 @@ tr = np.zeros(2048, dtype=np.int64)
 for _ in range(2):
     rc = L.dsabf_debug_trace(B._h, ctypes.c_void_p(x.data_ptr()), 32, ctypes.c_void_p(out.data_ptr()), tr.ctypes.data_as(ctypes.c_void_p))
 assert rc == 0
-t = tr.reshape(128, 16)[:, 4:14]
-names = ["top->full_ok", "full_ok->loaded", "loaded->fence+syncwarp", "->arrive(acc_empty)", "->token/math_start", "block0 math", "block1 math",
-         "->arrive(go)", "->finish(shfl+store)", "finish->next top"]
+t = tr.reshape(128, 16)[:, 4:12]
+names = ["top->full_ok", "full_ok->loaded", "loaded->fence+syncwarp", "->arrive(acc_empty)", "->math_start", "block0 math", "block1 math (+ shuffle, store)",
+         "end->next top"]
 sel = t[24:120]
 d = np.diff(sel, axis=1)
-nxt = t[25:121, 0] - t[24:120, 9]
+nxt = t[25:121, 0] - t[24:120, 7]
 print("mean clocks per phase (stages 24..119), lib =", os.environ.get("DSABF_LIB", "default"))
-for i in range(9):
-    print("  %-28s %7.1f  (min %d max %d)" % (names[i], d[:, i].mean(), d[:, i].min(), d[:, i].max()))
-print("  %-28s %7.1f  (min %d max %d)" % (names[9], nxt.mean(), nxt.min(), nxt.max()))
-print("  period (top to top)          %7.1f" % np.diff(t[24:121, 0]).mean())
+for i in range(7):
+    print("  %-30s %7.1f  (min %d max %d)" % (names[i], d[:, i].mean(), d[:, i].min(), d[:, i].max()))
+print("  %-30s %7.1f  (min %d max %d)" % (names[7], nxt.mean(), nxt.min(), nxt.max()))
+print("  period (top to top)            %7.1f" % np.diff(t[24:121, 0]).mean())
 print("MMA issuer: wait_start acquired issued (first rows):")
 m = tr.reshape(128, 16)[40:48, 0:3]
 print((m - m[0, 0]).tolist())
