@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 from conftest import ROOT
 
@@ -80,3 +81,17 @@ def test_dm_plan_matches_oracle(oracle):
     d = bf.dm_delays(dms[::25], freq)
     assert d.dtype == np.int32 and np.array_equal(d, oracle.dm_delays(dms[::25], freq))
     assert d[0].max() == 0 and d[-1, 0] == int(4.15 * dms[::25][-1] * (1.28 ** -2 - 1.53 ** -2) / (0.131 * 16))
+
+
+def test_experiment_patches_still_apply():
+    """tools/experiments/ keeps the dropped kernel variants as patches against the product source; they must not rot
+    silently (checked only in a git checkout: the GPU box gets a snapshot without .git)."""
+    import shutil
+    import subprocess
+    if not os.path.isdir(os.path.join(ROOT, ".git")) or not shutil.which("git"):
+        pytest.skip("not a git checkout")
+    exp = os.path.join(ROOT, "tools", "experiments")
+    for patch, reverse in (("r02_mix_and_turns.patch", False), ("r02_epilogue_switches_removed.patch", True)):
+        cmd = ["git", "apply", "--check"] + (["-R"] if reverse else []) + [os.path.join(exp, patch)]
+        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
+        assert r.returncode == 0, (patch, r.stderr[-400:])
