@@ -25,5 +25,8 @@ for i in range(7):
 print("  %-30s %7.1f  (min %d max %d)" % (names[7], nxt.mean(), nxt.min(), nxt.max()))
 print("  period (top to top)            %7.1f" % np.diff(t[24:121, 0]).mean())
 print("MMA issuer: wait_start acquired issued (first rows):")
-m = tr.reshape(128, 16)[40:48, 0:3]
-print((m - m[0, 0]).tolist())
+m = tr.reshape(128, 16)[40:56, 0:3]
+T = tr.reshape(128, 16)
+for a in range(40, 56):
+    print("  acc %d: issuer %s | epilogue warp: top %d full_ok %d loaded %d arrived %d end %d" % (a, (T[a, 0:3] - m[0, 0]).tolist(),
+          T[a, 4] - m[0, 0], T[a, 5] - m[0, 0], T[a, 6] - m[0, 0], T[a, 8] - m[0, 0], T[a, 11] - m[0, 0]))
